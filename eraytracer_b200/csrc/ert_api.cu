@@ -1,0 +1,738 @@
+// C ABI of the B200-native eraytracer hot path (include/ert_b200.h).
+// Host side: scene flattening to SoA, BVH build, upload, launches, band placement.
+// No CPU rendering path exists in this library.
+#include "../../include/ert_b200.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "ert_device.cuh"
+
+using namespace ert;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    g_err = buf;
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? ERT_ERR_NO_DEVICE : ERT_ERR_CUDA;
+}
+#define CU(call)                                                  \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);     \
+    } while (0)
+
+// Host copy of the flattened scene (kept so ert_scene_clone needs no rebuild).
+struct HostScene {
+    ert_camera camera;
+    std::vector<double> lights;        // [n][9]
+    std::vector<double> planes, plane_mat;
+    std::vector<int> plane_order;
+    std::vector<double> tris, tri_mat;
+    std::vector<int> tri_order;
+    std::vector<double> sph_exact;     // [n][4]
+    std::vector<double> sph_mat;       // [n][6]
+    std::vector<int> sph_order;
+    std::vector<float> sph_filter;     // [n][4]
+    std::vector<float> leaf_filter;    // [n][4]
+    Bvh bvh;
+    float r_max = 0, pad_c_max = 0, eta_c_max = 0, abs_max = 0;
+    int n_lights = 0, n_planes = 0, n_tris = 0, n_spheres = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    void *fb = nullptr;
+    size_t fb_cap = 0;
+    unsigned long long *counters_dev = nullptr;
+    unsigned long long *counters_host = nullptr;   // pinned
+    ert_render_params params{};
+    bool has_frame = false;
+    bool busy = false;
+    int local_rows = 0;
+    ert_stats stats{};
+    int pending_error = ERT_OK;
+    std::string pending_msg;
+};
+
+}  // namespace
+
+struct ert_scene {
+    int device = 0;
+    HostScene host;
+    DevScene dev{};
+    std::vector<void *> allocs;
+    Slot slots[ERT_MAX_SLOTS];
+    std::mutex mu;
+};
+
+namespace {
+
+bool finite3(const double *v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+bool finite_mat(const ert_material &m)
+{
+    return finite3(m.colour) && std::isfinite(m.specular_power) && std::isfinite(m.shininess) &&
+           std::isfinite(m.reflectivity);
+}
+void push_mat(std::vector<double> &v, const ert_material &m)
+{
+    v.insert(v.end(), {m.colour[0], m.colour[1], m.colour[2], m.specular_power, m.shininess, m.reflectivity});
+}
+float f_up(double x)
+{
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+// FP32 filter sphere {fl(c), R}: R >= r^2 with the slack the stage-1 bound needs
+// (DESIGN.md "Filter bounds"): r^2 (1 + 2^-18) + 16 r eta_c + 4 eta_c^2 / u.
+void make_filter_sphere(const double *c, double r, float out[4], float &pad_c, float &eta_c)
+{
+    const double u = 5.9604644775390625e-8;
+    double eta = 0;
+    for (int a = 0; a < 3; a++) {
+        out[a] = (float)c[a];
+        eta = std::max(eta, std::fabs(c[a] - (double)out[a]));
+    }
+    eta *= 2.0;
+    r = std::fabs(r);
+    double pad = 16.0 * r * eta + 4.0 * eta * eta / u;
+    double R = r * r * (1.0 + 3.814697265625e-6) + pad;
+    out[3] = std::nextafterf(f_up(R), INFINITY);
+    pad_c = f_up(pad);
+    eta_c = f_up(eta);
+}
+
+int flatten(const ert_scene_desc *d, HostScene &h)
+{
+    if (!d) return fail(ERT_ERR_BADARG, "scene descriptor is NULL");
+    if (d->n_lights < 0 || d->n_spheres < 0 || d->n_triangles < 0 || d->n_planes < 0)
+        return fail(ERT_ERR_BADARG, "negative element count");
+    if ((d->n_lights && !d->lights) || (d->n_spheres && !d->spheres) || (d->n_triangles && !d->triangles) ||
+        (d->n_planes && !d->planes))
+        return fail(ERT_ERR_BADARG, "element table pointer is NULL");
+    if (d->n_spheres >= (1 << 28) || d->n_planes >= (1 << 28) || d->n_triangles >= (1 << 28) ||
+        d->n_lights >= (1 << 20))
+        return fail(ERT_ERR_BADARG, "too many elements");
+    const ert_camera &c = d->camera;
+    if (!finite3(c.location) || !std::isfinite(c.fov) || !std::isfinite(c.screen_width) ||
+        !std::isfinite(c.screen_height))
+        return fail(ERT_ERR_BADARG, "camera has a non-finite field");
+    h.camera = c;
+
+    // list positions must be distinct: they decide ties (erl:319) and the light fold order (erl:211)
+    {
+        std::vector<int32_t> all;
+        all.reserve((size_t)(d->n_lights + d->n_spheres + d->n_triangles + d->n_planes));
+        for (int64_t i = 0; i < d->n_lights; i++) all.push_back(d->lights[i].order);
+        for (int64_t i = 0; i < d->n_spheres; i++) all.push_back(d->spheres[i].order);
+        for (int64_t i = 0; i < d->n_triangles; i++) all.push_back(d->triangles[i].order);
+        for (int64_t i = 0; i < d->n_planes; i++) all.push_back(d->planes[i].order);
+        std::sort(all.begin(), all.end());
+        for (size_t i = 0; i < all.size(); i++) {
+            if (all[i] < 0) return fail(ERT_ERR_BADARG, "negative list position in `order`");
+            if (i && all[i] == all[i - 1]) return fail(ERT_ERR_BADARG, "duplicate list position in `order`");
+        }
+    }
+
+    // lights, in list order
+    std::vector<int64_t> lidx((size_t)d->n_lights);
+    for (int64_t i = 0; i < d->n_lights; i++) lidx[(size_t)i] = i;
+    std::sort(lidx.begin(), lidx.end(), [&](int64_t a, int64_t b) { return d->lights[a].order < d->lights[b].order; });
+    h.n_lights = (int)d->n_lights;
+    for (int64_t k : lidx) {
+        const ert_point_light &l = d->lights[k];
+        if (!finite3(l.diffuse_colour) || !finite3(l.location) || !finite3(l.specular_colour))
+            return fail(ERT_ERR_BADARG, "point_light has a non-finite field");
+        h.lights.insert(h.lights.end(), {l.diffuse_colour[0], l.diffuse_colour[1], l.diffuse_colour[2], l.location[0],
+                                         l.location[1], l.location[2], l.specular_colour[0], l.specular_colour[1],
+                                         l.specular_colour[2]});
+    }
+    h.n_planes = (int)d->n_planes;
+    for (int64_t i = 0; i < d->n_planes; i++) {
+        const ert_plane &p = d->planes[i];
+        if (!finite3(p.normal) || !std::isfinite(p.distance) || !finite_mat(p.material))
+            return fail(ERT_ERR_BADARG, "plane has a non-finite field");
+        h.planes.insert(h.planes.end(), {p.normal[0], p.normal[1], p.normal[2], p.distance});
+        push_mat(h.plane_mat, p.material);
+        h.plane_order.push_back(p.order);
+    }
+    h.n_tris = (int)d->n_triangles;
+    for (int64_t i = 0; i < d->n_triangles; i++) {
+        const ert_triangle &t = d->triangles[i];
+        if (!finite3(t.v1) || !finite3(t.v2) || !finite3(t.v3) || !finite_mat(t.material))
+            return fail(ERT_ERR_BADARG, "triangle has a non-finite field");
+        h.tris.insert(h.tris.end(), {t.v1[0], t.v1[1], t.v1[2], t.v2[0], t.v2[1], t.v2[2], t.v3[0], t.v3[1], t.v3[2]});
+        push_mat(h.tri_mat, t.material);
+        h.tri_order.push_back(t.order);
+    }
+    // spheres, sorted by list position so sphere index order == list order
+    std::vector<int64_t> sidx((size_t)d->n_spheres);
+    for (int64_t i = 0; i < d->n_spheres; i++) sidx[(size_t)i] = i;
+    bool sorted = true;
+    for (int64_t i = 1; i < d->n_spheres; i++)
+        if (d->spheres[i].order < d->spheres[i - 1].order) { sorted = false; break; }
+    if (!sorted)
+        std::sort(sidx.begin(), sidx.end(),
+                  [&](int64_t a, int64_t b) { return d->spheres[a].order < d->spheres[b].order; });
+    h.n_spheres = (int)d->n_spheres;
+    h.sph_exact.resize((size_t)h.n_spheres * 4);
+    h.sph_mat.resize((size_t)h.n_spheres * 6);
+    h.sph_order.resize((size_t)h.n_spheres);
+    h.sph_filter.resize((size_t)h.n_spheres * 4);
+    std::vector<double> centers((size_t)h.n_spheres * 3), radii((size_t)h.n_spheres);
+    for (int64_t k = 0; k < d->n_spheres; k++) {
+        const ert_sphere &s = d->spheres[sidx[(size_t)k]];
+        if (!finite3(s.center) || !std::isfinite(s.radius) || !finite_mat(s.material))
+            return fail(ERT_ERR_BADARG, "sphere has a non-finite field");
+        double *e = &h.sph_exact[(size_t)k * 4];
+        e[0] = s.center[0]; e[1] = s.center[1]; e[2] = s.center[2]; e[3] = s.radius;
+        double *m = &h.sph_mat[(size_t)k * 6];
+        m[0] = s.material.colour[0]; m[1] = s.material.colour[1]; m[2] = s.material.colour[2];
+        m[3] = s.material.specular_power; m[4] = s.material.shininess; m[5] = s.material.reflectivity;
+        h.sph_order[(size_t)k] = s.order;
+        float pad_c, eta_c;
+        make_filter_sphere(s.center, s.radius, &h.sph_filter[(size_t)k * 4], pad_c, eta_c);
+        h.pad_c_max = std::max(h.pad_c_max, pad_c);
+        h.eta_c_max = std::max(h.eta_c_max, eta_c);
+        float ar = f_up(std::fabs(s.radius));
+        h.r_max = std::max(h.r_max, ar);
+        for (int a = 0; a < 3; a++) {
+            centers[(size_t)k * 3 + a] = s.center[a];
+            h.abs_max = std::max(h.abs_max, f_up(std::fabs(s.center[a]) + std::fabs(s.radius)));
+        }
+        radii[(size_t)k] = s.radius;
+    }
+    build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh);
+    h.leaf_filter.resize((size_t)h.n_spheres * 4);
+    for (int64_t k = 0; k < h.n_spheres; k++)
+        memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
+    return ERT_OK;
+}
+
+template <typename T>
+int upload(ert_scene *s, const std::vector<T> &v, const T **out)
+{
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    void *p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return ERT_OK;
+}
+
+int upload_scene(ert_scene *s)
+{
+    HostScene &h = s->host;
+    DevScene &d = s->dev;
+    int rc;
+    CU(cudaSetDevice(s->device));
+    d.n_lights = h.n_lights; d.n_planes = h.n_planes; d.n_tris = h.n_tris; d.n_spheres = h.n_spheres;
+#define UP(vec, field, T)                                                         \
+    do {                                                                          \
+        const T *p__;                                                             \
+        if ((rc = upload<T>(s, vec, &p__)) != ERT_OK) return rc;                  \
+        d.field = reinterpret_cast<decltype(d.field)>(p__);                       \
+    } while (0)
+    UP(h.lights, lights, double);
+    UP(h.planes, planes, double);
+    UP(h.plane_mat, plane_mat, double);
+    UP(h.plane_order, plane_order, int);
+    UP(h.tris, tris, double);
+    UP(h.tri_mat, tri_mat, double);
+    UP(h.tri_order, tri_order, int);
+    UP(h.sph_exact, sph_exact, double);
+    UP(h.sph_mat, sph_mat, double);
+    UP(h.sph_order, sph_order, int);
+    UP(h.sph_filter, sph_filter, float);
+    UP(h.leaf_filter, leaf_filter, float);
+    UP(h.bvh.leaf_prim, leaf_sph, int);
+    UP(h.bvh.nodes, nodes, BvhNode);
+#undef UP
+    d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
+    for (int i = 0; i < ERT_MAX_SLOTS; i++) {
+        Slot &sl = s->slots[i];
+        CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&sl.ev0));
+        CU(cudaEventCreate(&sl.ev1));
+        CU(cudaEventCreate(&sl.ev2));
+        CU(cudaMalloc(&sl.counters_dev, CNT_N * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&sl.counters_host, CNT_N * sizeof(unsigned long long)));
+    }
+    // opt in to the 64 KB double buffer of the tiled kernel
+    CU(cudaFuncSetAttribute(render_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            2 * kTileSpheres * 16));
+    CU(cudaFuncSetAttribute(render_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            2 * kTileSpheres * 16));
+    return ERT_OK;
+}
+
+void destroy(ert_scene *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (int i = 0; i < ERT_MAX_SLOTS; i++) {
+        Slot &sl = s->slots[i];
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        if (sl.fb) cudaFree(sl.fb);
+        if (sl.counters_dev) cudaFree(sl.counters_dev);
+        if (sl.counters_host) cudaFreeHost(sl.counters_host);
+        if (sl.ev0) cudaEventDestroy(sl.ev0);
+        if (sl.ev1) cudaEventDestroy(sl.ev1);
+        if (sl.ev2) cudaEventDestroy(sl.ev2);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    for (void *p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+size_t bytes_per_channel(int format) { return format == ERT_FMT_RGB8 ? 1 : (format == ERT_FMT_F32 ? 4 : 8); }
+
+// rows of this part and their count; band b -> part b % n_parts
+int local_rows_of(const ert_render_params &p)
+{
+    if (p.n_parts <= 1 || p.band_rows <= 0) return p.height;
+    int rows = 0;
+    int n_bands = (p.height + p.band_rows - 1) / p.band_rows;
+    for (int b = p.part; b < n_bands; b += p.n_parts) rows += std::min(p.band_rows, p.height - b * p.band_rows);
+    return rows;
+}
+
+int check_params(const ert_render_params *p)
+{
+    if (!p) return fail(ERT_ERR_BADARG, "render params are NULL");
+    if (p->width <= 0 || p->height <= 0) return fail(ERT_ERR_BADARG, "width and height must be > 0 (erl:89)");
+    if (p->depth < 0) return fail(ERT_ERR_BADARG, "recursion depth must be >= 0");
+    if (p->format < ERT_FMT_RGB8 || p->format > ERT_FMT_F64) return fail(ERT_ERR_BADARG, "unknown output format");
+    if (p->accel < ERT_ACCEL_AUTO || p->accel > ERT_ACCEL_BVH) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (p->n_parts > 1 && p->band_rows > 0 && (p->part < 0 || p->part >= p->n_parts))
+        return fail(ERT_ERR_BADARG, "part must be in [0, n_parts)");
+    if (p->band_rows < 0) return fail(ERT_ERR_BADARG, "band_rows must be >= 0");
+    return ERT_OK;
+}
+
+int pick_accel(const ert_scene *s, int requested)
+{
+    if (requested != ERT_ACCEL_AUTO) return requested;
+    if (s->host.n_spheres <= 16) return ERT_ACCEL_EXACT;
+    if (s->host.n_spheres <= 192) return ERT_ACCEL_LINEAR;
+    return ERT_ACCEL_BVH;
+}
+
+// device -> host placement of the part's rows inside the full frame
+int copy_part_to_host(ert_scene *s, Slot &sl, const ert_render_params &p, void *host_frame, size_t host_bytes,
+                      uint64_t *bytes_out)
+{
+    size_t row_bytes = (size_t)p.width * 3 * bytes_per_channel(p.format);
+    size_t need = row_bytes * (size_t)p.height;
+    if (host_bytes < need) return fail(ERT_ERR_BADARG, "host frame buffer is smaller than width*height*3 elements");
+    unsigned char *dst = (unsigned char *)host_frame;
+    const unsigned char *src = (const unsigned char *)sl.fb;
+    uint64_t total = 0;
+    if (p.n_parts <= 1 || p.band_rows <= 0) {
+        CU(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, sl.stream));
+        total = need;
+    } else {
+        int n_bands = (p.height + p.band_rows - 1) / p.band_rows;
+        int full_bands_total = p.height / p.band_rows;           // bands with band_rows rows
+        // own full bands: b = part, part + n_parts, ... < full_bands_total
+        int own_full = full_bands_total > p.part ? (full_bands_total - p.part + p.n_parts - 1) / p.n_parts : 0;
+        size_t band_bytes = row_bytes * (size_t)p.band_rows;
+        if (own_full > 0) {
+            CU(cudaMemcpy2DAsync(dst + (size_t)p.part * band_bytes, band_bytes * (size_t)p.n_parts, src, band_bytes,
+                                 band_bytes, (size_t)own_full, cudaMemcpyDeviceToHost, sl.stream));
+            total += band_bytes * (size_t)own_full;
+        }
+        // a partial last band, if this part owns it
+        int last = n_bands - 1;
+        if (n_bands > full_bands_total && last % p.n_parts == p.part) {
+            size_t rows = (size_t)(p.height - last * p.band_rows);
+            CU(cudaMemcpyAsync(dst + (size_t)last * band_bytes, src + (size_t)own_full * band_bytes, rows * row_bytes,
+                               cudaMemcpyDeviceToHost, sl.stream));
+            total += rows * row_bytes;
+        }
+    }
+    if (bytes_out) *bytes_out = total;
+    (void)s;
+    return ERT_OK;
+}
+
+template <bool COUNT>
+void launch_render(int accel, dim3 grid, cudaStream_t st, const DevScene &d, const FrameParams &fp)
+{
+    switch (accel) {
+    case ERT_ACCEL_EXACT: render_free_kernel<1, COUNT><<<grid, 256, 0, st>>>(d, fp); break;
+    case ERT_ACCEL_LINEAR: render_tiled_kernel<COUNT><<<grid, 256, 2 * kTileSpheres * 16, st>>>(d, fp); break;
+    default: render_free_kernel<3, COUNT><<<grid, 256, 0, st>>>(d, fp); break;
+    }
+}
+
+int finish_slot(ert_scene *s, Slot &sl)
+{
+    if (!sl.busy) return ERT_OK;
+    cudaError_t e = cudaStreamSynchronize(sl.stream);
+    sl.busy = false;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    float k = 0, t = 0;
+    cudaEventElapsedTime(&k, sl.ev0, sl.ev1);
+    cudaEventElapsedTime(&t, sl.ev0, sl.ev2);
+    sl.stats.kernel_ms = k;
+    sl.stats.total_ms = t;
+    sl.stats.rays = sl.counters_host[CNT_RAYS];
+    sl.stats.sphere_filter_tests = sl.counters_host[CNT_FILTER];
+    sl.stats.box_tests = sl.counters_host[CNT_BOX];
+    sl.stats.exact_sphere_tests = sl.counters_host[CNT_EXACT_SPH];
+    sl.stats.exact_other_tests = sl.counters_host[CNT_EXACT_OTHER];
+    (void)s;
+    return ERT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ert_abi_version(void) { return ERT_ABI_VERSION; }
+
+const char *ert_last_error(void) { return g_err.c_str(); }
+
+int ert_device_count(int *count)
+{
+    if (!count) return fail(ERT_ERR_BADARG, "count is NULL");
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    *count = n;
+    return ERT_OK;
+}
+
+static int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (n <= 0) return fail(ERT_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(ERT_ERR_BADARG, "device index out of range");
+    return ERT_OK;
+}
+
+int ert_scene_create(const ert_scene_desc *desc, int device, ert_scene **out)
+{
+    if (!out) return fail(ERT_ERR_BADARG, "out is NULL");
+    *out = nullptr;
+    ert_scene *s = new (std::nothrow) ert_scene();
+    if (!s) return fail(ERT_ERR_NOMEM, "out of host memory");
+    s->device = device;
+    int rc;
+    try {
+        rc = flatten(desc, s->host);
+    } catch (const std::bad_alloc &) {
+        delete s;
+        return fail(ERT_ERR_NOMEM, "out of host memory while flattening the scene");
+    }
+    if (rc != ERT_OK) { delete s; return rc; }
+    if ((rc = check_device(device)) != ERT_OK) { delete s; return rc; }
+    if ((rc = upload_scene(s)) != ERT_OK) {
+        std::string keep = g_err;
+        destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return ERT_OK;
+}
+
+int ert_scene_clone(const ert_scene *src, int device, ert_scene **out)
+{
+    if (!src || !out) return fail(ERT_ERR_BADARG, "NULL argument");
+    *out = nullptr;
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    ert_scene *s = new (std::nothrow) ert_scene();
+    if (!s) return fail(ERT_ERR_NOMEM, "out of host memory");
+    s->device = device;
+    try {
+        s->host = src->host;
+    } catch (const std::bad_alloc &) {
+        delete s;
+        return fail(ERT_ERR_NOMEM, "out of host memory");
+    }
+    if ((rc = upload_scene(s)) != ERT_OK) {
+        std::string keep = g_err;
+        destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return ERT_OK;
+}
+
+int ert_scene_destroy(ert_scene *scene)
+{
+    if (!scene) return ERT_OK;
+    destroy(scene);
+    return ERT_OK;
+}
+
+int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot, void *host_frame,
+                     size_t host_frame_bytes)
+{
+    if (!scene) return fail(ERT_ERR_BADARG, "scene is NULL");
+    int rc;
+    if ((rc = check_params(params)) != ERT_OK) return rc;
+    if (slot < 0 || slot >= ERT_MAX_SLOTS) return fail(ERT_ERR_BADARG, "slot out of range");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    CU(cudaSetDevice(scene->device));
+    Slot &sl = scene->slots[slot];
+    if ((rc = finish_slot(scene, sl)) != ERT_OK) return rc;
+
+    const ert_render_params &p = *params;
+    const ert_camera &cam = p.camera ? *p.camera : scene->host.camera;
+    if (!finite3(cam.location) || !std::isfinite(cam.fov) || !std::isfinite(cam.screen_width) ||
+        !std::isfinite(cam.screen_height))
+        return fail(ERT_ERR_BADARG, "camera has a non-finite field");
+
+    FrameParams fp{};
+    fp.width = p.width; fp.height = p.height; fp.depth = p.depth; fp.format = p.format;
+    fp.band_rows = p.band_rows; fp.n_parts = p.n_parts <= 1 ? 1 : p.n_parts; fp.part = p.part;
+    if (fp.n_parts == 1 || p.band_rows <= 0) { fp.n_parts = 1; fp.part = 0; fp.band_rows = 0; }
+    fp.local_rows = local_rows_of(p);
+    fp.cam[0] = cam.location[0]; fp.cam[1] = cam.location[1]; fp.cam[2] = cam.location[2];
+    // focal_length/2 (erl:483-484) with the host libm's tan, as BEAM's math:tan would
+    fp.focal = cam.screen_width / (2 * tan(cam.fov * (M_PI / 180) / 2));
+    fp.screen_w = cam.screen_width; fp.screen_h = cam.screen_height;
+
+    size_t fb_bytes = (size_t)std::max(fp.local_rows, 1) * (size_t)p.width * 3 * bytes_per_channel(p.format);
+    if (sl.fb_cap < fb_bytes) {
+        if (sl.fb) CU(cudaFree(sl.fb));
+        sl.fb = nullptr; sl.fb_cap = 0;
+        CU(cudaMalloc(&sl.fb, fb_bytes));
+        sl.fb_cap = fb_bytes;
+    }
+    fp.out = sl.fb;
+    fp.counters = sl.counters_dev;
+
+    sl.params = p;
+    sl.params.camera = nullptr;
+    sl.local_rows = fp.local_rows;
+    sl.stats = ert_stats{};
+    int accel = pick_accel(scene, p.accel);
+    sl.stats.accel_used = accel;
+    sl.stats.pixels = (uint64_t)fp.local_rows * (uint64_t)p.width;
+    sl.stats.h2d_bytes = sizeof(DevScene) + sizeof(FrameParams);   // kernel parameters of this frame
+
+    CU(cudaMemsetAsync(sl.counters_dev, 0, CNT_N * sizeof(unsigned long long), sl.stream));
+    CU(cudaEventRecord(sl.ev0, sl.stream));
+    if (fp.local_rows > 0) {
+        dim3 grid((unsigned)((p.width + 31) / 32), (unsigned)((fp.local_rows + 7) / 8));
+        if (p.flags & ERT_FLAG_COUNT_TESTS) launch_render<true>(accel, grid, sl.stream, scene->dev, fp);
+        else launch_render<false>(accel, grid, sl.stream, scene->dev, fp);
+        CU(cudaGetLastError());
+        sl.stats.gpu_launches = 1;
+    }
+    CU(cudaEventRecord(sl.ev1, sl.stream));
+    CU(cudaMemcpyAsync(sl.counters_host, sl.counters_dev, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       sl.stream));
+    sl.has_frame = true;
+    sl.busy = true;
+    if (host_frame && fp.local_rows > 0) {
+        uint64_t bytes = 0;
+        if ((rc = copy_part_to_host(scene, sl, p, host_frame, host_frame_bytes, &bytes)) != ERT_OK) {
+            std::string keep = g_err;
+            cudaStreamSynchronize(sl.stream);
+            sl.busy = false;
+            g_err = keep;
+            return rc;
+        }
+        sl.stats.d2h_bytes = bytes;
+    }
+    CU(cudaEventRecord(sl.ev2, sl.stream));
+    return ERT_OK;
+}
+
+int ert_wait(ert_scene *scene, int slot)
+{
+    if (!scene) return fail(ERT_ERR_BADARG, "scene is NULL");
+    if (slot < 0 || slot >= ERT_MAX_SLOTS) return fail(ERT_ERR_BADARG, "slot out of range");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    CU(cudaSetDevice(scene->device));
+    return finish_slot(scene, scene->slots[slot]);
+}
+
+int ert_render(ert_scene *scene, const ert_render_params *params, void *host_frame, size_t host_frame_bytes)
+{
+    if (!host_frame) return fail(ERT_ERR_BADARG, "host_frame is NULL");
+    int rc = ert_render_async(scene, params, 0, host_frame, host_frame_bytes);
+    if (rc != ERT_OK) return rc;
+    return ert_wait(scene, 0);
+}
+
+int ert_download(ert_scene *scene, int slot, void *host_frame, size_t host_frame_bytes)
+{
+    if (!scene || !host_frame) return fail(ERT_ERR_BADARG, "NULL argument");
+    if (slot < 0 || slot >= ERT_MAX_SLOTS) return fail(ERT_ERR_BADARG, "slot out of range");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    CU(cudaSetDevice(scene->device));
+    Slot &sl = scene->slots[slot];
+    int rc;
+    if ((rc = finish_slot(scene, sl)) != ERT_OK) return rc;
+    if (!sl.has_frame) return fail(ERT_ERR_BADARG, "nothing has been rendered on this slot");
+    uint64_t bytes = 0;
+    if (sl.local_rows > 0) {
+        if ((rc = copy_part_to_host(scene, sl, sl.params, host_frame, host_frame_bytes, &bytes)) != ERT_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(sl.stream));
+    sl.stats.d2h_bytes = bytes;
+    return ERT_OK;
+}
+
+int ert_get_stats(ert_scene *scene, int slot, ert_stats *out)
+{
+    if (!scene || !out) return fail(ERT_ERR_BADARG, "NULL argument");
+    if (slot < 0 || slot >= ERT_MAX_SLOTS) return fail(ERT_ERR_BADARG, "slot out of range");
+    std::lock_guard<std::mutex> lock(scene->mu);
+    *out = scene->slots[slot].stats;
+    return ERT_OK;
+}
+
+int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int accel, int32_t *order_out,
+                   double *t_out)
+{
+    if (!scene || (n_rays > 0 && (!rays6 || !order_out || !t_out))) return fail(ERT_ERR_BADARG, "NULL argument");
+    if (n_rays < 0) return fail(ERT_ERR_BADARG, "negative ray count");
+    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_BVH) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (n_rays == 0) return ERT_OK;
+    std::lock_guard<std::mutex> lock(scene->mu);
+    CU(cudaSetDevice(scene->device));
+    accel = pick_accel(scene, accel);
+    double *d_rays = nullptr, *d_t = nullptr;
+    int *d_ord = nullptr;
+    cudaStream_t st = scene->slots[0].stream;
+    int rc = ERT_OK;
+    cudaError_t e;
+#define TRY(call)                                         \
+    do {                                                  \
+        if ((e = (call)) != cudaSuccess) {                \
+            rc = cuda_fail(e, #call);                     \
+            goto done;                                    \
+        }                                                 \
+    } while (0)
+    TRY(cudaMalloc(&d_rays, (size_t)n_rays * 6 * sizeof(double)));
+    TRY(cudaMalloc(&d_t, (size_t)n_rays * sizeof(double)));
+    TRY(cudaMalloc(&d_ord, (size_t)n_rays * sizeof(int)));
+    TRY(cudaMemcpyAsync(d_rays, rays6, (size_t)n_rays * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        unsigned blocks = (unsigned)((n_rays + 255) / 256);
+        switch (accel) {
+        case ERT_ACCEL_EXACT: trace_rays_kernel<1><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        case ERT_ACCEL_LINEAR: trace_rays_kernel<2><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        default: trace_rays_kernel<3><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        }
+    }
+    TRY(cudaGetLastError());
+    TRY(cudaMemcpyAsync(order_out, d_ord, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(t_out, d_t, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+#undef TRY
+done:
+    if (d_rays) cudaFree(d_rays);
+    if (d_t) cudaFree(d_t);
+    if (d_ord) cudaFree(d_ord);
+    return rc;
+}
+
+int ert_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(ERT_ERR_BADARG, "out is NULL");
+    *out = nullptr;
+    CU(cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return ERT_OK;
+}
+int ert_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return ERT_OK;
+}
+int ert_host_register(void *p, size_t bytes)
+{
+    if (!p) return fail(ERT_ERR_BADARG, "pointer is NULL");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return ERT_OK;
+}
+int ert_host_unregister(void *p)
+{
+    if (p) CU(cudaHostUnregister(p));
+    return ERT_OK;
+}
+
+int ert_fp32_peak(int device, double *lane_instr_per_s)
+{
+    if (!lane_instr_per_s) return fail(ERT_ERR_BADARG, "out is NULL");
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8;
+    float *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(float)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const int iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(a));
+        fp32_peak_kernel<<<blocks, 256>>>(out, iters, 1.0f + rep);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double rate = (double)blocks * 256.0 * iters * kPeakFfmaPerIter / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, rate);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    *lane_instr_per_s = best;
+    return ERT_OK;
+}
+
+int ert_l2_flush(int device)
+{
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    CU(cudaSetDevice(device));
+    static thread_local void *buf[16] = {nullptr};
+    const size_t bytes = (size_t)256 << 20;
+    if (device >= 16) return fail(ERT_ERR_BADARG, "device index too large for the flush buffers");
+    if (!buf[device]) CU(cudaMalloc(&buf[device], bytes));
+    l2_flush_kernel<<<1184, 256>>>((uint4 *)buf[device], bytes / 16);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return ERT_OK;
+}
+
+}  // extern "C"
