@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and frame ms of the eraytracer hot path on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W [--workload c4] [--impl reference]
+
+A "step" is one frame of the workload.  The scene is uploaded once before timing
+(BASELINE.json north_star: "uploads a flattened SoA scene once"); `value` is timed with the
+frame kept on the device, `e2e` through the synchronous C-ABI call ert_render() into a
+(pinned / shared) HOST frame with the camera passed in every step.  With N > 1 (torchrun,
+one rank per GPU) the SAME frame is split into interleaved row bands, one part per rank
+(strong scaling, no collective on the data path); times are CUDA-event times, max over ranks.
+
+--impl reference times the CPU oracle (a C restatement of raytracer.erl; the reference
+itself needs Erlang/OTP, which this image does not have) on all host cores over a bounded
+lattice of pixels of the same frame.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, scene, width, height, depth)
+    "c1": ("C1 demo scene 32x24 depth 1 (run.sh)", "demo", 32, 24, 1),
+    "c2": ("C2 demo scene 1920x1080 depth 1 (run-concurrent.sh depth)", "demo", 1920, 1080, 1),
+    "c2d5": ("C2 demo scene 1920x1080 depth 5 (raytrace/1 default depth)", "demo", 1920, 1080, 5),
+    "c3": ("C3 synthetic 10k-sphere scene 3840x2160, 3 point lights, depth 5", "c3", 3840, 2160, 5),
+    "c4": ("C4 synthetic 1M-sphere scene 3840x2160, 3 point lights, depth 5, BVH", "c4", 3840, 2160, 5),
+    "c5": ("C5 demo scene 7680x4320 depth 1, camera pose k of 64 per step", "demo", 7680, 4320, 1),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_scene(kind):
+    from eraytracer_b200 import scene as sc
+    if kind == "demo":
+        return sc.flatten(sc.demo_scene())
+    return sc.synthetic_scene(kind)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.tmp = None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        clocks, maxes, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                if int(parts[0]) != self.gpu_index:
+                    continue
+                clocks.append(float(parts[1]))
+                maxes.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.tmp.close()
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if clocks:
+            out["sm_mhz"] = statistics.median(clocks)
+            out["sm_max_mhz"] = max(maxes)
+            out["power_w_max"] = max(power)
+            out["samples"] = len(clocks)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+def lattice(width, height, nx, ny):
+    xs = ((np.arange(nx) + 0.5) * width / nx).astype(np.int32)
+    ys = ((np.arange(ny) + 0.5) * height / ny).astype(np.int32)
+    gx, gy = np.meshgrid(xs, ys)
+    return gx.reshape(-1).astype(np.int32), gy.reshape(-1).astype(np.int32)
+
+
+class CpuArm:
+    """The oracle (oracle/oracle.c) on all host cores over a lattice of pixels."""
+
+    def __init__(self, flat, width, height, depth):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle_scene_from_flat
+        from oracle import orc
+        self.orc = orc
+        self.cam, self.kind, self.f = oracle_scene_from_flat(flat)
+        self.w, self.h, self.depth = width, height, depth
+        self.cores = os.cpu_count() or 1
+
+    def run(self, nx, ny):
+        px = lattice(self.w, self.h, nx, ny)
+        t0 = time.perf_counter()
+        _, rays, _ = self.orc.render(self.cam, self.kind, self.f, self.w, self.h, self.depth,
+                                     pixels=px, nthreads=self.cores)
+        dt = time.perf_counter() - t0
+        return rays, dt, len(px[0])
+
+    def sized_sample(self, budget_s):
+        """Picks a lattice that costs about budget_s seconds (capped at the full frame)."""
+        nx, ny = 8, 4
+        rays, dt, npx = self.run(nx, ny)
+        per_px = max(dt / npx, 1e-7)
+        target = int(min(self.w * self.h, max(32, budget_s / per_px)))
+        aspect = self.w / self.h
+        ny = max(1, int((target / aspect) ** 0.5))
+        nx = max(1, int(ny * aspect))
+        return min(nx, self.w), min(ny, self.h)
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    desc, kind, w, h, depth = WORKLOADS[args.workload]
+    flat = build_scene(kind)
+    arm = CpuArm(flat, w, h, depth)
+    total_steps = args.steps + args.warmup
+    budget = min(10.0, 150.0 / max(total_steps, 1))
+    nx, ny = arm.sized_sample(budget)
+    for _ in range(args.warmup):
+        arm.run(nx, ny)
+    rays_total, t_total, npx = 0, 0.0, 0
+    for _ in range(args.steps):
+        rays, dt, npx = arm.run(nx, ny)
+        rays_total += rays
+        t_total += dt
+    value = rays_total / t_total / 1e6
+    sample = "%dx%d pixel lattice (%d px) of the %dx%d frame per step" % (nx, ny, npx, w, h)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "width": w, "height": h, "depth": depth,
+                   "sample": sample, "rays": "unique rays (one per nearest-object scan)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
+                         "sample": sample,
+                         "note": "C restatement of raytracer.erl (oracle/oracle.c), not BEAM: "
+                                 "Erlang/OTP is not installed in this image"},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- GPU arm
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from eraytracer_b200 import _lib, multigpu
+    from eraytracer_b200 import scene as sc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device is visible; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(value, op):
+        if world == 1:
+            return value
+        t = torch.tensor([float(value)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t.item())
+
+    desc, kind, w, h, depth = WORKLOADS[args.workload]
+    accel = args.accel
+    t0 = time.perf_counter()
+    flat = build_scene(kind)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    dev = flat.upload(local_rank)
+    t_upload = time.perf_counter() - t0
+    log("[rank %d] scene built in %.2fs, flattened+BVH+uploaded in %.2fs" % (rank, t_gen, t_upload))
+
+    n_parts = world
+    band_rows = multigpu.default_band_rows(h, world)
+    fmt = "rgb8"
+    frame_bytes = w * h * 3
+    if world == 1:
+        host = _lib.PinnedFrame(frame_bytes)
+        host_ptr = host.ptr
+        shared = None
+    else:
+        name = "ert_b200_frame_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            shared = multigpu.SharedFrame(name, frame_bytes, create=True)
+        barrier()
+        if rank != 0:
+            shared = multigpu.SharedFrame(name, frame_bytes, create=False)
+        shared.register()
+        host_ptr = shared.ptr
+
+    def camera_for(step):
+        return sc.pose_camera(step % 64) if args.workload == "c5" else None
+
+    common = dict(fmt=fmt, accel=accel, band_rows=band_rows, n_parts=n_parts, part=rank)
+    peak = _lib.fp32_peak(local_rank)
+
+    # warm-up through the full end-to-end path
+    for i in range(max(args.warmup, 0)):
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), host_ptr=host_ptr,
+                         host_bytes=frame_bytes, **common)
+        dev.wait(0)
+
+    # instrumented (untimed) run: test counters for the roofline accounting
+    dev.render_async(w, h, depth, slot=0, flags=_lib.FLAG_COUNT_TESTS, camera=camera_for(0), **common)
+    dev.wait(0)
+    counted = dev.stats(0)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- timed block A: frame stays on the device (inputs resident in HBM) ----
+    barrier()
+    kernel_ms, rays = 0.0, 0
+    launches = 0
+    for i in range(args.steps):
+        _lib.l2_flush(local_rank)
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), **common)
+        dev.wait(0)
+        st = dev.stats(0)
+        kernel_ms += st["kernel_ms"]
+        rays += st["rays"]
+        launches += st["gpu_launches"]
+    barrier()
+    kernel_ms_max = reduce(kernel_ms, "max")
+    rays_all = reduce(rays, "sum")
+    launches_all = int(reduce(launches, "sum"))
+
+    # ---- timed block B: end to end through ert_render() with a host frame ----
+    barrier()
+    e2e_wall, e2e_dev_ms, d2h = 0.0, 0.0, 0
+    lib = _lib.load()
+    import ctypes
+    for i in range(args.steps):
+        _lib.l2_flush(local_rank)
+        p = dev._params(w, h, depth, fmt, accel, band_rows, n_parts, rank, 0, camera_for(i) or flat.camera)
+        t1 = time.perf_counter()
+        _lib.check(lib.ert_render(dev.handle, ctypes.byref(p), host_ptr, frame_bytes))
+        e2e_wall += time.perf_counter() - t1
+        st = dev.stats(0)
+        e2e_dev_ms += st["total_ms"]
+        d2h += st["d2h_bytes"]
+    barrier()
+    e2e_wall_max = reduce(e2e_wall, "max")
+    e2e_dev_ms_max = reduce(e2e_dev_ms, "max")
+    d2h_all = reduce(d2h, "sum")
+    clocks = sampler.stop()
+
+    # the assembled host frame must equal a single-GPU render of the whole frame
+    assembled_ok = None
+    if world > 1 and rank == 0 and args.workload != "c5":
+        full, _ = dev.render(w, h, depth, fmt=fmt, accel=accel)
+        assembled_ok = bool(np.array_equal(full, shared.array(np.uint8, (h, w, 3))))
+
+    if rank == 0:
+        steps = max(args.steps, 1)
+        ms_per_step = kernel_ms_max / steps
+        value = rays_all / steps / (ms_per_step * 1e-3) / 1e6
+        e2e_ms = 1e3 * e2e_wall_max / steps
+        e2e_value = rays_all / steps / (e2e_ms * 1e-3) / 1e6
+        # roofline of the dominant kernel (rank 0's launch): FP32 filter work / kernel time
+        lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10
+        k_s = (kernel_ms / steps) * 1e-3
+        achieved = lane_instr / k_s
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 decisions+shading, f32 conservative filters", "data": "synthetic",
+            "config": {
+                "workload": desc, "width": w, "height": h, "depth": depth, "accel": counted["accel_used"],
+                "spheres": int(len(flat.spheres)), "lights": int(len(flat.lights)),
+                "rays": "unique rays (one per nearest-object scan: primary + reflection + shadow)",
+                "rays_per_frame": rays_all / steps,
+                "partition": ("row bands of %d rows dealt round-robin to %d GPUs" % (band_rows, world)
+                              if world > 1 else "whole frame on one GPU"),
+                "l2": "flushed between steps (256 MiB device write outside the timed events)",
+                "output": "RGB8 framebuffer (min(trunc(C*255),255) fused)",
+                "scene_upload_s": t_upload,
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+                    "device_ms_per_step": e2e_dev_ms_max / steps,
+                    "h2d_bytes_per_step": int(counted["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(d2h_all / steps),
+                    "what": "ert_render() per step: camera + params in, kernel, pinned D2H of the RGB8 rows"},
+            "gpu_launches": launches_all,
+            "roofline": {
+                "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "kernel": "render_free_kernel<BVH>" if counted["accel_used"] == "bvh" else
+                          ("render_tiled_kernel" if counted["accel_used"] == "linear" else "render_free_kernel<EXACT>"),
+                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test, "
+                              "counts from an instrumented run of the same frame on rank 0",
+                "box_tests": int(counted["box_tests"]), "sphere_filter_tests": int(counted["sphere_filter_tests"]),
+                "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
+                "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
+                "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
+            },
+        }
+        if assembled_ok is not None:
+            line["config"]["assembled_frame_equals_single_gpu"] = assembled_ok
+        if world == 1 and not args.no_cpu_baseline:
+            arm = CpuArm(flat, w, h, depth)
+            nx, ny = arm.sized_sample(args.cpu_budget)
+            c_rays, c_dt, c_px = arm.run(nx, ny)
+            line["cpu_baseline"] = {
+                "value": c_rays / c_dt / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
+                "sample": "%dx%d pixel lattice (%d px) of the %dx%d frame, %.1f s" % (nx, ny, c_px, w, h, c_dt),
+                "note": "C restatement of raytracer.erl (oracle/oracle.c), not BEAM: Erlang/OTP is not installed"}
+        print(json.dumps(line), flush=True)
+
+    if shared is not None:
+        barrier()
+        shared.close()
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh"))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sample at N=1")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        log("bench.py: warm-up raised to 3 steps (timing rule)")
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
+        return subprocess.call(cmd)
+    return gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -172,8 +172,8 @@ SYNTH_CONFIGS = {
 
 def synthetic_scene(name="c3", n_spheres=None, seed=None):
     """Random-sphere scene of SURVEY §8(d): camera (0,0,-2) fov 90 screen 4x2.25, the demo
-    floor plane, three point lights, n spheres.  Every value is rounded to float32 so the
-    CPU oracle and the GPU start from identical inputs.  List order: lights, spheres, plane."""
+    floor plane, three point lights, n spheres.  Every value is rounded to float32 so that a
+    double-precision CPU evaluation and the GPU start from identical inputs.  List order: lights, spheres, plane."""
     n0, xr, yr, zr, rr, seed0 = SYNTH_CONFIGS[name]
     n = n0 if n_spheres is None else int(n_spheres)
     seed = seed0 if seed is None else seed

@@ -419,7 +419,7 @@ EXPORT int orc_quantise(double c, int max_value)
 typedef struct {
     const double *cam;
     scene_t sc;
-    int width, height, depth, retrace;
+    int width, height, depth, retrace, nthreads;
     int64_t npix;
     const int32_t *xs, *ys;     /* NULL => full frame, row-major (erl:90-99) */
     double *out;                /* npix*3 */
@@ -432,7 +432,9 @@ static void *worker(void *arg)
 {
     job_t *j = (job_t *)arg;
     counters_t c = {0, 0};
-    const int64_t chunk = 64;
+    int64_t chunk = j->npix / ((int64_t)j->nthreads * 16);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 64) chunk = 64;
     for (;;) {
         int64_t lo, hi;
         pthread_mutex_lock(&j->mu);
@@ -481,6 +483,7 @@ EXPORT int orc_render(const double *cam, int n, const int32_t *kind, const doubl
     pthread_mutex_init(&j.mu, NULL);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
+    j.nthreads = nthreads;
     for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, worker, &j);
     worker(&j);
     for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);

@@ -1,0 +1,331 @@
+"""GPU edge cases and properties: everything the reference's semantics make awkward."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import eraytracer_b200 as ert
+from eraytracer_b200 import _lib, multigpu, raytracer
+from eraytracer_b200 import scene as sc
+from helpers import (assert_double_parity, assert_image_parity, oracle_frame,
+                     oracle_scene_from_flat, quantise)
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+ACCELS = ("exact", "linear", "bvh")
+CAM = ('camera', ('vector', 0, 0, -2), ('vector', 0, 0, 0), 90, ('screen', 4, 3))
+L1 = ('point_light', ('colour', 1, 1, 0.5), ('vector', 5, -2, 0), ('colour', 1, 1, 1))
+L2 = ('point_light', ('colour', 1, 0, 0.5), ('vector', -10, 0, 7), ('colour', 1, 0, 0.5))
+
+
+def mat(c=(1, 0.5, 0), sp=4, sh=0.25, refl=0.5):
+    return ('material', ('colour',) + tuple(c), sp, sh, refl)
+
+
+def check_scene(scene, w=64, h=48, depth=4, accels=ACCELS, rays_equal=True):
+    flat = sc.flatten(scene)
+    dev = flat.upload(0)
+    ref, ref_rays, _ = oracle_frame(flat, w, h, depth)
+    try:
+        for accel in accels:
+            frame, st = dev.render(w, h, depth, fmt="f64", accel=accel)
+            assert_double_parity(frame, ref)
+            assert np.array_equal(quantise(frame), quantise(ref)), accel
+            # a zero-reflectivity hit ends the path on the GPU (0 * child adds nothing), so
+            # such scenes trace fewer rays than the reference would
+            assert st["rays"] == ref_rays if rays_equal else st["rays"] <= ref_rays, accel
+    finally:
+        dev.close()
+    return ref
+
+
+@pytest.mark.parametrize("accel", ACCELS)
+def test_depth_zero_is_black_without_tracing(gpu, accel):
+    dev = sc.flatten(sc.demo_scene()).upload(0)
+    frame, st = dev.render(16, 12, 0, fmt="f64", accel=accel)
+    assert not frame.any() and st["rays"] == 0
+    dev.close()
+
+
+def test_scene_without_lights_is_black(gpu):
+    scene = [e for e in sc.demo_scene() if e[0] != 'point_light']
+    ref = check_scene(scene, 16, 12, 5)
+    assert not ref.any()
+
+
+def test_camera_only_scene(gpu):
+    ref = check_scene([CAM], 8, 8, 3)
+    assert not ref.any()
+
+
+def test_lights_only_scene(gpu):
+    check_scene([CAM, L1, L2], 8, 8, 3)
+
+
+def test_unknown_elements_keep_their_list_positions(gpu):
+    scene = sc.demo_scene()
+    scene.insert(3, ('fog', 40))
+    scene.insert(1, 'an_atom')
+    scene.append(('colour', 1, 1, 1))
+    a = check_scene(scene, 32, 24, 3)
+    b, _, _ = oracle_frame(sc.flatten(sc.demo_scene()), 32, 24, 3)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (31, 9), (65, 7), (257, 3)])
+def test_odd_image_sizes(gpu, w, h):
+    check_scene(sc.demo_scene(), w, h, 3)
+
+
+def test_bad_arguments_raise_badarg(gpu):
+    dev = sc.flatten(sc.demo_scene()).upload(0)
+    for w, h, d in ((0, 4, 1), (4, 0, 1), (-3, 4, 1), (4, 4, -1)):
+        with pytest.raises(ert.BadArg):
+            dev.render(w, h, d, out=np.zeros((1, 1, 3)))
+    with pytest.raises(ert.BadArg):
+        dev.render(8, 8, 1, band_rows=4, n_parts=2, part=2)
+    with pytest.raises(ert.BadArg):
+        dev.render(8, 8, 1, out=np.zeros((4, 8, 3)))          # host frame too small
+    order, t = dev.trace_rays(np.zeros((0, 6)))
+    assert len(order) == 0
+    dev.close()
+    lights = np.zeros(2, dtype=_lib.LIGHT_DT)                  # duplicate list positions
+    with pytest.raises(ert.BadArg):
+        _lib.Scene.create(sc.camera_struct(CAM), lights, np.zeros(0, _lib.SPHERE_DT),
+                          np.zeros(0, _lib.TRIANGLE_DT), np.zeros(0, _lib.PLANE_DT))
+    sp = np.zeros(1, dtype=_lib.SPHERE_DT)
+    sp['radius'] = np.nan
+    with pytest.raises(ert.BadArg):
+        _lib.Scene.create(sc.camera_struct(CAM), np.zeros(0, _lib.LIGHT_DT), sp,
+                          np.zeros(0, _lib.TRIANGLE_DT), np.zeros(0, _lib.PLANE_DT))
+
+
+def test_equal_distance_goes_to_the_earlier_list_element(gpu):
+    """Strict '>' at erl:319: two coincident objects, the first one listed is hit."""
+    red = ('plane', ('vector', 0, -1, 0), 5, mat((1, 0, 0), 1, 0, 0.2))
+    blue = ('plane', ('vector', 0, -1, 0), 5, mat((0, 0, 1), 1, 0, 0.2))
+    s_a = ('sphere', 3, ('vector', 0, 0, 9), mat((1, 0, 0)))
+    s_b = ('sphere', 3, ('vector', 0, 0, 9), mat((0, 1, 0)))
+    a = check_scene([CAM, L1, red, blue, s_a, s_b], 48, 36, 3)
+    b = check_scene([CAM, L1, blue, red, s_b, s_a], 48, 36, 3)
+    # a later coincident duplicate never wins a scan (primary or shadow): dropping it changes nothing
+    assert np.array_equal(a, check_scene([CAM, L1, red, s_a], 48, 36, 3))
+    assert np.array_equal(b, check_scene([CAM, L1, blue, s_b], 48, 36, 3))
+    assert not np.array_equal(a, b)
+    # the demo triangle's edge lies in the floor plane: exact ties between triangle and plane
+    check_scene(sc.demo_scene(), 196, 147, 5)
+
+
+def test_origin_inside_a_sphere_misses_it(gpu):
+    """erl:381 wants both roots >= 0: a camera inside a sphere does not see it."""
+    big = ('sphere', 50, ('vector', 0, 0, 0), mat((1, 1, 1)))
+    small = ('sphere', 2, ('vector', 0, 0, 10), mat((0, 1, 0), 20, 1, 0.3))
+    ref = check_scene([CAM, L1, big, small], 48, 36, 3)
+    assert ref.any()
+
+
+def test_unnormalised_plane_normal_and_non_unit_reflection_rays(gpu):
+    """erl:476 returns the stored normal as is, so bounce directions leave the unit sphere and
+    the 'divide by 2, not 2A' roots (erl:379-380) matter.  All strategies must follow."""
+    floor = ('plane', ('vector', 0, -2, 0), 10, mat((1, 1, 1), 1, 0, 0.6))
+    wall = ('plane', ('vector', 0.3, 0, -1.7), 40, mat((0.2, 0.4, 1), 4, 0.5, 0.5))
+    spheres = [('sphere', 1.5 + 0.1 * i, ('vector', -6 + 3 * i, 2 - 0.5 * i, 8 + i), mat((0.2 * i, 1, 0.5), 20, 1, 0.4))
+               for i in range(5)]
+    check_scene([CAM, L1, L2, floor, wall] + spheres, 96, 72, 5)
+
+
+def test_negative_colours_and_byte_clamp(gpu):
+    weird = ('sphere', 4, ('vector', 0, 0, 10), mat((-1, 0.5, 2), 2, 0.5, 0.1))
+    flat = sc.flatten([CAM, L1, weird])
+    dev = flat.upload(0)
+    ref, _, _ = oracle_frame(flat, 32, 24, 2)
+    f64, _ = dev.render(32, 24, 2, fmt="f64")
+    assert_double_parity(f64, ref)
+    assert ref.min() < 0
+    rgb8, _ = dev.render(32, 24, 2, fmt="rgb8")
+    assert np.array_equal(rgb8.astype(np.int64), np.clip(quantise(ref), 0, 255))
+    dev.close()
+
+
+def test_centres_and_radii_that_are_not_float32_values(gpu):
+    rng = np.random.default_rng(3)
+    spheres = [('sphere', float(rng.uniform(0.3, 1.7)), ('vector', float(rng.uniform(-8, 8)), float(rng.uniform(-6, 4)),
+                float(rng.uniform(6, 30))), mat(tuple(rng.uniform(0, 1, 3)), 20, 0.5, float(rng.uniform(0, 0.7))))
+               for _ in range(300)]
+    floor = ('plane', ('vector', 0, -1, 0), 5, mat((1, 1, 1), 1, 0, 0.1))
+    check_scene([CAM, L1, L2] + spheres + [floor], 96, 72, 4)
+
+
+def test_far_away_scene_and_camera(gpu):
+    """Large coordinates stress the FP32 filters' absolute error terms."""
+    rng = np.random.default_rng(5)
+    off = np.array([4000.25, -1500.5, 9000.125])
+    cam = ('camera', ('vector',) + tuple(off + [0, 0, -2]), ('vector', 0, 0, 0), 90, ('screen', 4, 3))
+    light = ('point_light', ('colour', 1, 1, 1), ('vector',) + tuple(off + [5, -20, 0]), ('colour', 1, 1, 1))
+    spheres = [('sphere', float(rng.uniform(0.3, 1.5)),
+                ('vector',) + tuple(off + [rng.uniform(-10, 10), rng.uniform(-8, 4), rng.uniform(6, 40)]),
+                mat(tuple(rng.uniform(0, 1, 3)), 4, 0.5, 0.5)) for _ in range(400)]
+    floor = ('plane', ('vector', 0, -1, 0), 5 - 1500.5, mat((1, 1, 1), 1, 0, 0.3))
+    check_scene([cam, light] + spheres + [floor], 96, 72, 4)
+
+
+def test_huge_and_tiny_spheres(gpu):
+    spheres = [('sphere', 1000, ('vector', 0, -1010, 50), mat((1, 0.2, 0.2), 4, 0.5, 0.3)),
+               ('sphere', 0.01, ('vector', 0.1, 0.1, 1), mat((0, 1, 0), 4, 0.5, 0.3)),
+               ('sphere', 300, ('vector', 400, 0, 900), mat((0, 0.3, 1), 50, 1, 0.6))]
+    spheres += [('sphere', 0.05, ('vector', -1 + 0.07 * i, 0.5, 2 + 0.01 * i), mat((1, 1, 0), 1, 0, 0)) for i in range(40)]
+    floor = ('plane', ('vector', 0, -1, 0), 5, mat((1, 1, 1), 1, 0, 0.2))
+    check_scene([CAM, L1, L2] + spheres + [floor], 96, 72, 4, rays_equal=False)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_mixed_scenes(gpu, seed):
+    rng = np.random.default_rng(100 + seed)
+    def v(lo, hi):
+        return ('vector',) + tuple(float(x) for x in rng.uniform(lo, hi, 3))
+    def m():
+        return mat(tuple(float(x) for x in rng.uniform(0, 1, 3)), float(rng.choice([1, 2.5, 4, 20])),
+                   float(rng.uniform(0, 1)), float(rng.choice([0, 0.3, 0.7, 1.0])))
+    elems = [('point_light', ('colour',) + tuple(rng.uniform(0, 1, 3)), v(-20, 20), ('colour',) + tuple(rng.uniform(0, 1, 3)))
+             for _ in range(int(rng.integers(1, 5)))]
+    n_s = int(rng.choice([5, 60, 700]))
+    elems += [('sphere', float(rng.uniform(0.2, 2.5)), ('vector', float(rng.uniform(-12, 12)), float(rng.uniform(-9, 5)),
+               float(rng.uniform(2, 40))), m()) for _ in range(n_s)]
+    elems += [('triangle', v(-10, 10), v(-10, 10), v(-10, 10), m()) for _ in range(int(rng.integers(0, 12)))]
+    elems += [('plane', ('vector', float(rng.uniform(-0.3, 0.3)), -1, float(rng.uniform(-0.3, 0.3))), float(rng.uniform(3, 8)), m())
+              for _ in range(int(rng.integers(0, 3)))]
+    order = rng.permutation(len(elems))
+    scene = [CAM] + [elems[i] for i in order]
+    check_scene(scene, 80, 60, 4, rays_equal=False)
+
+
+def test_band_parts_assemble_the_whole_frame(gpu):
+    flat = sc.flatten(sc.demo_scene())
+    dev = flat.upload(0)
+    w, h, depth = 64, 47, 3
+    whole, st = dev.render(w, h, depth, fmt="f64")
+    for band_rows, n_parts in ((5, 3), (8, 2), (1, 7), (16, 4)):
+        frame = np.full((h, w, 3), np.nan)
+        rays = 0
+        for part in range(n_parts):
+            _, s = dev.render(w, h, depth, fmt="f64", band_rows=band_rows, n_parts=n_parts, part=part, out=frame)
+            assert s["pixels"] == len(multigpu.part_rows(h, band_rows, n_parts, part)) * w
+            rays += s["rays"]
+        assert np.array_equal(frame, whole)
+        assert rays == st["rays"]
+    dev.close()
+
+
+def test_async_slots_with_per_frame_cameras(gpu):
+    flat = sc.flatten(sc.demo_scene())
+    dev = flat.upload(0)
+    w, h = 96, 54
+    frames = [_lib.PinnedFrame(w * h * 3) for _ in range(_lib.MAX_SLOTS)]
+    cams = [sc.pose_camera(k) for k in range(_lib.MAX_SLOTS)]
+    for k in range(_lib.MAX_SLOTS):
+        dev.render_async(w, h, 1, slot=k, fmt="rgb8", camera=cams[k], host_ptr=frames[k].ptr, host_bytes=w * h * 3)
+    for k in range(_lib.MAX_SLOTS):
+        dev.wait(k)
+        got = frames[k].array(np.uint8, (h, w, 3))
+        flat_k = sc.FlatScene(cams[k], flat.lights, flat.spheres, flat.triangles, flat.planes)
+        ref, _, _ = oracle_frame(flat_k, w, h, 1)
+        assert np.array_equal(got.astype(np.int64), np.clip(quantise(ref), 0, 255))
+    for f in frames:
+        f.close()
+    dev.close()
+
+
+def test_scene_clone_renders_identically(gpu):
+    flat = sc.synthetic_scene("c3", n_spheres=2000)
+    a = flat.upload(0)
+    b = a.clone(0)
+    fa, _ = a.render(160, 90, 3, fmt="f64", accel="bvh")
+    fb, _ = b.render(160, 90, 3, fmt="f64", accel="bvh")
+    assert np.array_equal(fa, fb)
+    a.close()
+    b.close()
+
+
+def test_committed_golden_fixture(gpu):
+    """GPU against tests/golden/demo_images.json (no oracle build needed for this one)."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "demo_images.json")))
+    dev = sc.flatten(sc.demo_scene()).upload(0)
+    for key, img in g["images"].items():
+        for accel in ACCELS:
+            rgb8, st = dev.render(img["width"], img["height"], img["depth"], fmt="rgb8", accel=accel)
+            assert rgb8.reshape(-1).tolist() == img["rgb8"], (key, accel)
+            assert st["rays"] == img["rays"]
+    dev.close()
+
+
+def test_host_mirror_writes_the_reference_ppm(gpu, tmp_path):
+    """raytrace/5 through tracing_function(gpu) (raytracer.erl:723-733) writes the P3 file the
+    oracle's pixel list would give."""
+    out = tmp_path / "traced.ppm"
+    assert raytracer.go(32, 24, str(out), 1, 'gpu') == 'ok'
+    flat = sc.flatten(sc.demo_scene())
+    ref, _, _ = oracle_frame(flat, 32, 24, 1)
+    want = "P3\n32 24\n255\n" + "".join("%d %d %d " % tuple(px) for px in quantise(ref).reshape(-1, 3).tolist())
+    assert out.read_text() == want
+    pixels = raytracer.raytraced_pixel_list_gpu(4, 3, sc.demo_scene(), 5)
+    assert [p[0] for p in pixels] == list(range(12))
+    assert quantise(np.array([p[1] for p in pixels])).tolist() == json.load(
+        open(os.path.join(os.path.dirname(__file__), "golden", "demo_images.json")))["appendix_a"]["4x3_d5"]
+    assert raytracer.standalone(["16", "12", str(out), "1", "gpu"]) == 'ok'
+    multi = raytracer.raytraced_pixel_list_gpu_distributed(32, 24, sc.demo_scene(), 1)
+    single = raytracer.raytraced_pixel_list_gpu(32, 24, sc.demo_scene(), 1)
+    assert multi == single
+
+
+# ---- BASELINE.json's full sizes: size-independent properties -------------------------------
+def test_c3_full_4k_bvh_equals_linear_on_a_row_subset_and_oracle_on_a_lattice(gpu):
+    flat = sc.synthetic_scene("c3")
+    dev = flat.upload(0)
+    w, h, depth = 3840, 2160, 5
+    full, st = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    assert st["pixels"] == w * h and st["rays"] > 8 * w * h
+    sub = np.zeros_like(full)
+    dev.render(w, h, depth, fmt="f64", accel="linear", band_rows=1, n_parts=108, part=37, out=sub)
+    rows = multigpu.part_rows(h, 1, 108, 37)
+    assert np.array_equal(sub[rows], full[rows])
+    xs = ((np.arange(48) + 0.5) * w / 48).astype(np.int32)
+    ys = ((np.arange(27) + 0.5) * h / 27).astype(np.int32)
+    gx, gy = np.meshgrid(xs, ys)
+    ref, _, _ = oracle_frame(flat, w, h, depth, pixels=(gx.reshape(-1), gy.reshape(-1)))
+    got = full[gy.reshape(-1), gx.reshape(-1)]
+    assert_double_parity(got, ref)
+    assert np.array_equal(quantise(got), quantise(ref))
+    rgb8, _ = dev.render(w, h, depth, fmt="rgb8", accel="bvh")
+    assert np.array_equal(rgb8.astype(np.int64), np.clip(quantise(full), 0, 255))
+    dev.close()
+
+
+def test_c4_full_4k_bvh_equals_linear_scan_and_oracle_samples(gpu):
+    """Config C4: the BVH must return the linear scan's hits on the 1M-sphere scene."""
+    flat = sc.synthetic_scene("c4")
+    dev = flat.upload(0)
+    w, h, depth = 3840, 2160, 5
+    full, st = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    assert st["accel_used"] == "bvh" and st["rays"] > 8 * w * h
+    # one row in 1080 through the tiled linear scan (1M spheres per ray)
+    sub = np.zeros_like(full)
+    dev.render(w, h, depth, fmt="f64", accel="linear", band_rows=1, n_parts=1080, part=700, out=sub)
+    rows = multigpu.part_rows(h, 1, 1080, 700)
+    assert np.array_equal(sub[rows], full[rows])
+    # ray batch: BVH == linear scan on (t bits, list position)
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = np.stack([rng.uniform(-210, 210, n), rng.uniform(-160, 5, n), rng.uniform(-5, 410, n)], axis=1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], axis=1)
+    ob, tb = dev.trace_rays(rays, accel="bvh")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    assert np.array_equal(ob, ol) and np.array_equal(tb, tl)
+    # the CPU oracle on a few pixels (each costs ~16 rays x 1M spheres)
+    xs = np.array([400, 1900, 3000, 1200], dtype=np.int32)
+    ys = np.array([300, 1500, 900, 2000], dtype=np.int32)
+    ref, _, _ = oracle_frame(flat, w, h, depth, pixels=(xs, ys))
+    assert_double_parity(full[ys, xs], ref)
+    dev.close()
