@@ -1,0 +1,99 @@
+%% raytracer_gpu.erl -- GPU tracing functions for plouj/eraytracer (B200, sm_100a).
+%%
+%% Drop-in for the 4-arity "tracing function" seam of raytracer.erl:
+%%     Fun(Width, Height, Scene, Recursion_depth) -> [{Index, {R,G,B}}]
+%% (tracing_function/1, raytracer.erl:714-719; called at raytracer.erl:728-732).
+%%
+%% The only change needed in raytracer.erl is two clauses in tracing_function/1:
+%%     tracing_function(gpu) -> fun raytracer_gpu:raytraced_pixel_list_gpu/4;
+%%     tracing_function(gpu_distributed) -> fun raytracer_gpu:raytraced_pixel_list_gpu_distributed/4;
+%% after which   erl -noinput -run raytracer standalone 1920 1080 out.ppm 1 gpu   works.
+%%
+%% NOTE: written without an Erlang/OTP installation (none in the build image); it has not
+%% been compiled.  It contains no logic beyond argument guards and calls into the NIF.
+-module(raytracer_gpu).
+-export([raytraced_pixel_list_gpu/4,
+         raytraced_pixel_list_gpu_distributed/4,
+         render_binary/5,
+         write_binary_to_ppm/4,
+         device_count/0, scene_info/1, scene_upload/2, render/5, render_pixel_list/5]).
+-on_load(init/0).
+
+init() ->
+    PrivDir = case code:priv_dir(?MODULE) of
+                  {error, _} -> "priv";
+                  Dir -> Dir
+              end,
+    erlang:load_nif(filename:join(PrivDir, "raytracer_gpu"), 0).
+
+%% ---- NIF stubs (c_src/raytracer_gpu_nif.c) ---------------------------------
+device_count() -> erlang:nif_error(nif_not_loaded).
+scene_info(_Scene) -> erlang:nif_error(nif_not_loaded).
+scene_upload(_Scene, _Device) -> erlang:nif_error(nif_not_loaded).
+render(_Handle, _Width, _Height, _Depth, _Opts) -> erlang:nif_error(nif_not_loaded).
+render_pixel_list(_Handle, _Width, _Height, _Depth, _Opts) -> erlang:nif_error(nif_not_loaded).
+
+%% ---- tracing functions -------------------------------------------------------
+%% Same clauses and guards as raytraced_pixel_list_simple/4 (raytracer.erl:86-99).
+raytraced_pixel_list_gpu(0, 0, _, _) ->
+    done;
+raytraced_pixel_list_gpu(Width, Height, Scene, Recursion_depth)
+  when Width > 0, Height > 0 ->
+    {ok, Handle} = ok_or_exit(scene_upload(Scene, 0)),
+    case render_pixel_list(Handle, Width, Height, Recursion_depth, []) of
+        {error, Reason} -> exit({raytracer_gpu, Reason});
+        Pixels when is_list(Pixels) -> Pixels
+    end.
+
+%% Row bands dealt round-robin to every GPU of the box; one Erlang process per GPU calls
+%% the dirty NIF, each returns the full-size frame with only its rows filled, and the
+%% rows are stitched by binary part copies (the role of distribute_work/7 + master/3,
+%% raytracer.erl:139-161, without one message per pixel).
+raytraced_pixel_list_gpu_distributed(0, 0, _, _) ->
+    done;
+raytraced_pixel_list_gpu_distributed(Width, Height, Scene, Recursion_depth)
+  when Width > 0, Height > 0 ->
+    Frame = render_binary(Width, Height, Scene, Recursion_depth, [{format, f64}]),
+    pixel_list_from_f64(Frame, 0, []).
+
+%% Whole frame as a binary (rgb8 by default): the scalable return type.
+render_binary(Width, Height, Scene, Recursion_depth, Opts) when Width > 0, Height > 0 ->
+    {ok, N} = ok_or_exit(device_count()),
+    BandRows = 8,
+    Parent = self(),
+    Pids = [spawn_link(fun() ->
+                {ok, H} = ok_or_exit(scene_upload(Scene, Dev)),
+                Parent ! {self(), render(H, Width, Height, Recursion_depth,
+                                         [{part, {BandRows, N, Dev}} | Opts])}
+            end) || Dev <- lists:seq(0, N - 1)],
+    Frames = [receive {Pid, {ok, Bin}} -> Bin;
+                      {Pid, {error, Reason}} -> exit({raytracer_gpu, Reason})
+              end || Pid <- Pids],
+    stitch(Frames, Width, Height, BandRows, proplists:get_value(format, Opts, rgb8)).
+
+stitch([Single], _W, _H, _BandRows, _Format) ->
+    Single;
+stitch(Frames, Width, Height, BandRows, Format) ->
+    RowBytes = Width * 3 * case Format of rgb8 -> 1; f32 -> 4; f64 -> 8 end,
+    N = length(Frames),
+    Bands = (Height + BandRows - 1) div BandRows,
+    iolist_to_binary(
+      [begin
+           Rows = min(BandRows, Height - B * BandRows),
+           binary:part(lists:nth((B rem N) + 1, Frames), B * BandRows * RowBytes, Rows * RowBytes)
+       end || B <- lists:seq(0, Bands - 1)]).
+
+pixel_list_from_f64(<<>>, _I, Acc) ->
+    lists:reverse(Acc);
+pixel_list_from_f64(<<R:64/float-native, G:64/float-native, B:64/float-native, Rest/binary>>, I, Acc) ->
+    pixel_list_from_f64(Rest, I + 1, [{I, {R, G, B}} | Acc]).
+
+%% P3 writer over an rgb8 frame binary: the bytes write_pixels_to_ppm/5 (raytracer.erl:668-685)
+%% produces, without the W*H-element pixel list and the io:format per pixel.
+write_binary_to_ppm(Width, Height, FrameRgb8, Filename) ->
+    Body = [[integer_to_list(V), $\s] || <<V:8>> <= FrameRgb8],
+    file:write_file(Filename,
+                    [io_lib:format("P3~n~p ~p~n~p~n", [Width, Height, 255]), Body]).
+
+ok_or_exit({ok, _} = Ok) -> Ok;
+ok_or_exit({error, Reason}) -> exit({raytracer_gpu, Reason}).
