@@ -348,8 +348,9 @@ def gpu_arm(args, rank, world, local_rank):
             "roofline": {
                 "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": "render_free_kernel<BVH>" if counted["accel_used"] == "bvh" else
-                          ("render_tiled_kernel" if counted["accel_used"] == "linear" else "render_free_kernel<EXACT>"),
+                "kernel": {"bvh": "wf_trace_shadow + wf_trace_path (BVH traversal kernels of the wavefront)",
+                           "bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
+                           "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?"),
                 "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test, "
                               "counts from an instrumented run of the same frame on rank 0",
                 "box_tests": int(counted["box_tests"]), "sphere_filter_tests": int(counted["sphere_filter_tests"]),
@@ -386,7 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh"))
+    ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh", "bvh_mega"))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sample at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

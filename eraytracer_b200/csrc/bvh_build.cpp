@@ -61,6 +61,8 @@ struct Builder {
     int max_depth_seen = 0;
     std::atomic<int> live_tasks{0};
     int max_tasks = 1;
+    int leaf_max = kBvhLeafMax;
+    float trav_cost = 0.f;
 
     int32_t alloc() { return next.fetch_add(1); }
 
@@ -81,7 +83,7 @@ struct Builder {
                 chi[a] = std::max(chi[a], cen[3 * (size_t)p + a]);
             }
         }
-        if (count <= kBvhLeafMax) return me;
+        if (count <= 1 || (count <= leaf_max && trav_cost <= 0.f)) return me;
 
         int32_t mid = -1;
         if (depth < kSahMaxDepth) {
@@ -124,6 +126,11 @@ struct Builder {
                     if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
                 }
             }
+            // SAH termination: a small range stays a leaf when splitting does not pay
+            if (count <= leaf_max && best_axis >= 0) {
+                float area = n.box.half_area();
+                if (!(area > 0.f) || trav_cost + best_cost / area >= (float)count) return me;
+            }
             if (best_axis >= 0) {
                 float ext = chi[best_axis] - clo[best_axis];
                 float scale = NB / ext;
@@ -138,6 +145,7 @@ struct Builder {
                 mid = (int32_t)(it - idx.begin());
             }
         }
+        if ((mid <= first || mid >= first + count) && count <= leaf_max) return me;
         if (mid <= first || mid >= first + count) {
             // degenerate (coincident centroids) or too deep: split by index at the median
             // along the widest axis so depth stays logarithmic
@@ -175,8 +183,9 @@ inline int32_t leaf_code(int32_t first, int32_t count) { return ~((first << 3) |
 
 }  // namespace
 
-void build_sphere_bvh(const double *centers, const double *radii, int64_t n, Bvh &out)
+void build_sphere_bvh(const double *centers, const double *radii, int64_t n, Bvh &out, int leaf_max, float trav_cost)
 {
+    leaf_max = std::min(std::max(leaf_max, 1), 8);
     out.nodes.clear();
     out.leaf_prim.clear();
     out.depth = 0;
@@ -205,6 +214,8 @@ void build_sphere_bvh(const double *centers, const double *radii, int64_t n, Bvh
         }
         b.idx[(size_t)i] = (int32_t)i;
     }
+    b.leaf_max = leaf_max;
+    b.trav_cost = trav_cost;
     b.tmp.resize((size_t)2 * n + 2);
     b.max_tasks = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     int32_t root = b.build(0, (int32_t)n, 0);

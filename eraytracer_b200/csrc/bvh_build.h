@@ -21,7 +21,8 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
-constexpr int kBvhLeafMax = 4;      // spheres per leaf (<= 8 by the encoding)
+constexpr int kBvhLeafMax = 4;      // default spheres per leaf (<= 8 by the encoding)
+constexpr float kBvhTravCost = 0.f; // default SAH traversal cost (see build_sphere_bvh)
 constexpr int kSahMaxDepth = 30;    // below this depth splits fall back to the median (log2 n more levels)
 constexpr int kBvhStack = 64;       // traversal stack entries (depth <= 30 + log2(n) + 1)
 
@@ -32,6 +33,10 @@ struct Bvh {
 };
 
 // centers: n*3 doubles, radii: n doubles.  Boxes are [c-r, c+r] rounded outward to float.
-void build_sphere_bvh(const double *centers, const double *radii, int64_t n, Bvh &out);
+// leaf_max: largest leaf (1..8).  trav_cost: cost of visiting one inner node in units of one
+// ray/sphere filter test; a range of <= leaf_max spheres stays a leaf when the SAH says a
+// split would not pay (trav_cost <= 0: always split down to leaf_max, the round-1 behaviour).
+void build_sphere_bvh(const double *centers, const double *radii, int64_t n, Bvh &out, int leaf_max = kBvhLeafMax,
+                      float trav_cost = 0.f);
 
 }  // namespace ert

@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -15,6 +16,7 @@
 
 #include "bvh_build.h"
 #include "ert_device.cuh"
+#include "ert_wavefront.cuh"
 
 using namespace ert;
 
@@ -63,6 +65,12 @@ struct Slot {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     void *fb = nullptr;
     size_t fb_cap = 0;
+    // wavefront queues (ERT_ACCEL_BVH), allocated on first use
+    void *wf_mem = nullptr;
+    size_t wf_cap = 0;
+    unsigned int *wf_ctr = nullptr;
+    int wf_ctr_depth = 0;
+    unsigned int *wf_ctr_host = nullptr;           // pinned, for the early-out check of deep recursions
     unsigned long long *counters_dev = nullptr;
     unsigned long long *counters_host = nullptr;   // pinned
     ert_render_params params{};
@@ -78,6 +86,7 @@ struct Slot {
 
 struct ert_scene {
     int device = 0;
+    int wf_grid[4] = {0, 0, 0, 0};     // persistent grid sizes: path(first), path, shadow, shade
     HostScene host;
     DevScene dev{};
     std::vector<void *> allocs;
@@ -223,7 +232,14 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         }
         radii[(size_t)k] = s.radius;
     }
-    build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh);
+    {
+        // tuning knobs of the BVH builder (defaults are the measured best, DESIGN.md "BVH")
+        int leaf_max = kBvhLeafMax;
+        float trav_cost = kBvhTravCost;
+        if (const char *e = getenv("ERT_BVH_LEAF_MAX")) leaf_max = atoi(e);
+        if (const char *e = getenv("ERT_BVH_TRAV_COST")) trav_cost = (float)atof(e);
+        build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
+    }
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
@@ -271,6 +287,7 @@ int upload_scene(ert_scene *s)
     UP(h.bvh.leaf_prim, leaf_sph, int);
     UP(h.bvh.nodes, nodes, BvhNode);
 #undef UP
+    d.n_nodes = (int)h.bvh.nodes.size();
     d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
     for (int i = 0; i < ERT_MAX_SLOTS; i++) {
         Slot &sl = s->slots[i];
@@ -286,6 +303,19 @@ int upload_scene(ert_scene *s)
                             2 * kTileSpheres * 16));
     CU(cudaFuncSetAttribute(render_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             2 * kTileSpheres * 16));
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, s->device));
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false>, kWfThreads, 0));
+        s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false>, kWfThreads, 0));
+        s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false>, kWfThreads, 0));
+        s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
+        s->wf_grid[3] = prop.multiProcessorCount * std::max(nb, 1);
+    }
     return ERT_OK;
 }
 
@@ -297,6 +327,9 @@ void destroy(ert_scene *s)
         Slot &sl = s->slots[i];
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.fb) cudaFree(sl.fb);
+        if (sl.wf_mem) cudaFree(sl.wf_mem);
+        if (sl.wf_ctr) cudaFree(sl.wf_ctr);
+        if (sl.wf_ctr_host) cudaFreeHost(sl.wf_ctr_host);
         if (sl.counters_dev) cudaFree(sl.counters_dev);
         if (sl.counters_host) cudaFreeHost(sl.counters_host);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
@@ -326,7 +359,7 @@ int check_params(const ert_render_params *p)
     if (p->width <= 0 || p->height <= 0) return fail(ERT_ERR_BADARG, "width and height must be > 0 (erl:89)");
     if (p->depth < 0) return fail(ERT_ERR_BADARG, "recursion depth must be >= 0");
     if (p->format < ERT_FMT_RGB8 || p->format > ERT_FMT_F64) return fail(ERT_ERR_BADARG, "unknown output format");
-    if (p->accel < ERT_ACCEL_AUTO || p->accel > ERT_ACCEL_BVH) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (p->accel < ERT_ACCEL_AUTO || p->accel > ERT_ACCEL_BVH_MEGAKERNEL) return fail(ERT_ERR_BADARG, "unknown accel");
     if (p->n_parts > 1 && p->band_rows > 0 && (p->part < 0 || p->part >= p->n_parts))
         return fail(ERT_ERR_BADARG, "part must be in [0, n_parts)");
     if (p->band_rows < 0) return fail(ERT_ERR_BADARG, "band_rows must be >= 0");
@@ -385,8 +418,102 @@ void launch_render(int accel, dim3 grid, cudaStream_t st, const DevScene &d, con
     switch (accel) {
     case ERT_ACCEL_EXACT: render_free_kernel<1, COUNT><<<grid, 256, 0, st>>>(d, fp); break;
     case ERT_ACCEL_LINEAR: render_tiled_kernel<COUNT><<<grid, 256, 2 * kTileSpheres * 16, st>>>(d, fp); break;
-    default: render_free_kernel<3, COUNT><<<grid, 256, 0, st>>>(d, fp); break;
+    default: render_free_kernel<3, COUNT><<<grid, 256, 0, st>>>(d, fp); break;   // BVH megakernel (also depth 0)
     }
+}
+
+// ---- wavefront frame (ERT_ACCEL_BVH) ------------------------------------------------------
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
+{
+    int tiles_x = (fp.width + 7) / 8, tiles_y = (fp.local_rows + 3) / 4;
+    size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
+    if (n_pad >= ((size_t)1 << 31)) return fail(ERT_ERR_BADARG, "frame part has more than 2^31 pixels");
+    size_t L = (size_t)std::max(s->host.n_lights, 1);
+    // layout: C[3] W[1] q_ray[6] h_geo[9] doubles, then q_pid h_pid h_obj h_order ints, then lit bytes
+    size_t off = 0;
+    size_t o_dbl = off; off += align_up(n_pad * 19 * sizeof(double), 256);
+    size_t o_int = off; off += align_up(n_pad * 4 * sizeof(int), 256);
+    size_t o_lit = off; off += align_up(n_pad * L, 256);
+    if (sl.wf_cap < off) {
+        if (sl.wf_mem) CU(cudaFree(sl.wf_mem));
+        sl.wf_mem = nullptr; sl.wf_cap = 0;
+        cudaError_t e = cudaMalloc(&sl.wf_mem, off);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ERT_ERR_NOMEM, "out of device memory for the wavefront queues");
+        }
+        sl.wf_cap = off;
+    }
+    if (sl.wf_ctr_depth < fp.depth) {
+        if (sl.wf_ctr) CU(cudaFree(sl.wf_ctr));
+        sl.wf_ctr = nullptr; sl.wf_ctr_depth = 0;
+        CU(cudaMalloc(&sl.wf_ctr, (size_t)fp.depth * kWfCtr * sizeof(unsigned int)));
+        sl.wf_ctr_depth = fp.depth;
+    }
+    if (!sl.wf_ctr_host) CU(cudaMallocHost(&sl.wf_ctr_host, kWfCtr * sizeof(unsigned int)));
+    unsigned char *base = (unsigned char *)sl.wf_mem;
+    double *d = (double *)(base + o_dbl);
+    int *i = (int *)(base + o_int);
+    wf.n_pad = (int)n_pad;
+    wf.tiles_x = tiles_x;
+    wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.h_geo = d + 10 * n_pad;
+    wf.q_pid = i; wf.h_pid = i + n_pad; wf.h_obj = i + 2 * n_pad; wf.h_order = i + 3 * n_pad;
+    wf.lit = base + o_lit;
+    wf.ctr = sl.wf_ctr;
+    return ERT_OK;
+}
+
+template <bool COUNT>
+int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *launches)
+{
+    WfBuf wf{};
+    int rc;
+    if ((rc = wf_prepare(s, sl, fp, wf)) != ERT_OK) return rc;
+    cudaStream_t st = sl.stream;
+    const DevScene &d = s->dev;
+    CU(cudaMemsetAsync(wf.ctr, 0, (size_t)fp.depth * kWfCtr * sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(wf.C, 0, (size_t)wf.n_pad * 3 * sizeof(double), st));
+    uint64_t n = 0;
+    // ERT_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
+    static const bool debug_sync = getenv("ERT_DEBUG_SYNC") != nullptr;
+#define WF_CHECK(what)                                                                 \
+    do {                                                                               \
+        if (debug_sync) {                                                              \
+            cudaError_t e__ = cudaStreamSynchronize(st);                               \
+            if (e__ != cudaSuccess) {                                                  \
+                char buf__[128];                                                       \
+                snprintf(buf__, sizeof buf__, "%s (bounce %d)", what, b);              \
+                return cuda_fail(e__, buf__);                                          \
+            }                                                                          \
+        }                                                                              \
+    } while (0)
+    for (int b = 0; b < fp.depth; b++) {
+        if (b >= 8) {
+            // deep recursions: stop launching once the path queue has run dry
+            CU(cudaMemcpyAsync(sl.wf_ctr_host, wf.ctr + (size_t)(b - 1) * kWfCtr, kWfCtr * sizeof(unsigned int),
+                               cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
+        }
+        if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        n++;
+        WF_CHECK("wf_trace_path");
+        if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
+        wf_trace_shadow<COUNT><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
+        WF_CHECK("wf_trace_shadow");
+        wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
+        n += 2;
+        WF_CHECK("wf_shade");
+    }
+    wf_finalize<<<s->wf_grid[3], kWfThreads, 0, st>>>(fp, wf);
+    n++;
+    CU(cudaGetLastError());
+#undef WF_CHECK
+    *launches = n;
+    return ERT_OK;
 }
 
 int finish_slot(ert_scene *s, Slot &sl)
@@ -545,7 +672,13 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
 
     CU(cudaMemsetAsync(sl.counters_dev, 0, CNT_N * sizeof(unsigned long long), sl.stream));
     CU(cudaEventRecord(sl.ev0, sl.stream));
-    if (fp.local_rows > 0) {
+    if (fp.local_rows > 0 && accel == ERT_ACCEL_BVH && fp.depth > 0) {
+        uint64_t n = 0;
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, &n);
+        if (rc != ERT_OK) return rc;
+        sl.stats.gpu_launches = n;
+    } else if (fp.local_rows > 0) {
         dim3 grid((unsigned)((p.width + 31) / 32), (unsigned)((fp.local_rows + 7) / 8));
         if (p.flags & ERT_FLAG_COUNT_TESTS) launch_render<true>(accel, grid, sl.stream, scene->dev, fp);
         else launch_render<false>(accel, grid, sl.stream, scene->dev, fp);
@@ -622,7 +755,7 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
 {
     if (!scene || (n_rays > 0 && (!rays6 || !order_out || !t_out))) return fail(ERT_ERR_BADARG, "NULL argument");
     if (n_rays < 0) return fail(ERT_ERR_BADARG, "negative ray count");
-    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_BVH) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_BVH_MEGAKERNEL) return fail(ERT_ERR_BADARG, "unknown accel");
     if (n_rays == 0) return ERT_OK;
     std::lock_guard<std::mutex> lock(scene->mu);
     CU(cudaSetDevice(scene->device));
@@ -648,7 +781,8 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
         switch (accel) {
         case ERT_ACCEL_EXACT: trace_rays_kernel<1><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         case ERT_ACCEL_LINEAR: trace_rays_kernel<2><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
-        default: trace_rays_kernel<3><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        case ERT_ACCEL_BVH_MEGAKERNEL: trace_rays_kernel<3><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        default: trace_rays_kernel<4><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         }
     }
     TRY(cudaGetLastError());

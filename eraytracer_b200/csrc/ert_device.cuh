@@ -46,6 +46,7 @@ struct DevScene {
     const float4 *sph_filter;    // {fl(cx), fl(cy), fl(cz), R} — see make_filter_sphere()
     // BVH over spheres
     const BvhNode *nodes;
+    int n_nodes;
     const float4 *leaf_filter;   // filter spheres in leaf order
     const int *leaf_sph;         // leaf slot -> sphere index
     // filter constants of the scene
@@ -274,7 +275,8 @@ __device__ __forceinline__ void make_fray(const DevScene &sc, d3 O, d3 D, FRay &
 }
 
 // reference Distance of the incumbent -> filter-space cull distance (upper bound)
-__device__ __forceinline__ float cull_from(const FRay &f, const Hit &best)
+template <class R>
+__device__ __forceinline__ float cull_from(const R &f, const Hit &best)
 {
     if (best.obj < 0) return __int_as_float(0x7f800000);
     double s = best.t * f.inv_sqrt_a;
@@ -284,7 +286,8 @@ __device__ __forceinline__ float cull_from(const FRay &f, const Hit &best)
 
 // Stage 1: 10 FP32-pipe instructions (3 FADD, 1 FMUL, 6 FFMA) + 1 compare.
 // v = b^2 - (|oc|^2 - R);  accept iff !(v < -theta).
-__device__ __forceinline__ bool filter_stage1(const FRay &f, float4 s, float &b, float &v)
+template <class R>
+__device__ __forceinline__ bool filter_stage1(const R &f, float4 s, float &b, float &v)
 {
     float cx = s.x - f.ox, cy = s.y - f.oy, cz = s.z - f.oz;
     b = __fmaf_rn(f.dz, cz, __fmaf_rn(f.dy, cy, f.dx * cx));
@@ -294,7 +297,8 @@ __device__ __forceinline__ bool filter_stage1(const FRay &f, float4 s, float &b,
 }
 
 // Stage 2 (only for stage-1 survivors): behind-the-origin and beyond-the-incumbent culls.
-__device__ __forceinline__ bool filter_stage2(const FRay &f, float4 s, float b, float v, float cull)
+template <class R>
+__device__ __forceinline__ bool filter_stage2(const R &f, float4 s, float b, float v, float cull)
 {
     if (b < -f.bcull) return false;
     float arg = fmaxf(v, 0.f) + ERT_REL17 * (b * b + s.w) + f.pad2;
@@ -493,6 +497,39 @@ __device__ __forceinline__ void pix_prepare(const Pix &p, const DevScene &sc, Qu
     }
 }
 
+// hit normal by object kind (erl:388-390, 476, 448-451)
+__device__ __forceinline__ d3 hit_normal(const DevScene &sc, int obj, d3 P)
+{
+    int i = obj_index(obj);
+    switch (obj_type(obj)) {
+    case OBJ_SPHERE: {
+        double4 s = sc.sph_exact[i];
+        return vnormalize(vsub(P, mk(s.x, s.y, s.z)));
+    }
+    case OBJ_PLANE:
+        return mk(sc.planes[4 * i], sc.planes[4 * i + 1], sc.planes[4 * i + 2]);
+    default: {
+        const double *tr = sc.tris + 9 * i;
+        return vnormalize(vcross(mk(tr[0], tr[1], tr[2]), mk(tr[3], tr[4], tr[5])));
+    }
+    }
+}
+
+// LightColour (*) (Diffuse + Specular) of one unshadowed light (erl:225-247, 272-297);
+// D is the direction of the ray that hit.
+__device__ __forceinline__ d3 light_term(const double *l, const double *mat, d3 P, d3 N, d3 D)
+{
+    d3 lpos = mk(l[3], l[4], l[5]);
+    d3 ldir = vnormalize(vsub(lpos, P));
+    // diffuse_term erl:272-279
+    d3 diffuse = vscale(mk(mat[0], mat[1], mat[2]), max0(vdot(N, ldir)));
+    // specular_term erl:285-297
+    double base = max0(vdot(vnormalize(vadd(ldir, vneg(D))), N));
+    d3 specular = vscale(mk(l[6], l[7], l[8]), mat[4] * pow(base, mat[3]));
+    d3 contribution = vadd(diffuse, specular);                       // erl:225-238
+    return vscale(vcmul(mk(l[0], l[1], l[2]), contribution), 1.0);   // erl:243-247, shadow = 1
+}
+
 // Consumes the resolved query: shading of erl:209-252 in forward (weight-carrying) form.
 __device__ __forceinline__ void pix_consume(Pix &p, const DevScene &sc, const FrameParams &fp, const Query &q)
 {
@@ -504,21 +541,7 @@ __device__ __forceinline__ void pix_consume(Pix &p, const DevScene &sc, const Fr
         p.hit_obj = q.best.obj;
         p.hit_order = q.best.order;
         p.P = vadd(p.O, vscale(p.D, q.best.t));               // erl:384-387 / 443-447 / 471-475
-        int i = obj_index(p.hit_obj);
-        switch (obj_type(p.hit_obj)) {
-        case OBJ_SPHERE: {
-            double4 s = sc.sph_exact[i];
-            p.N = vnormalize(vsub(p.P, mk(s.x, s.y, s.z)));   // erl:388-390
-            break;
-        }
-        case OBJ_PLANE:
-            p.N = mk(sc.planes[4 * i], sc.planes[4 * i + 1], sc.planes[4 * i + 2]);   // erl:476
-            break;
-        default: {
-            const double *tr = sc.tris + 9 * i;
-            p.N = vnormalize(vcross(mk(tr[0], tr[1], tr[2]), mk(tr[3], tr[4], tr[5])));  // erl:448-451
-        }
-        }
+        p.N = hit_normal(sc, p.hit_obj, p.P);
         p.S = mk(0.0, 0.0, 0.0);
         if (L == 0) { p.alive = false; return; }
         p.phase = 1;
@@ -528,16 +551,7 @@ __device__ __forceinline__ void pix_consume(Pix &p, const DevScene &sc, const Fr
     const double *mat = material_ptr(sc, p.hit_obj);
     bool lit = q.need && q.best.obj == p.hit_obj;
     if (lit) {
-        const double *l = sc.lights + 9 * (p.phase - 1);
-        d3 lpos = mk(l[3], l[4], l[5]);
-        d3 ldir = vnormalize(vsub(lpos, p.P));
-        // diffuse_term erl:272-279
-        d3 diffuse = vscale(mk(mat[0], mat[1], mat[2]), max0(vdot(p.N, ldir)));
-        // specular_term erl:285-297
-        double base = max0(vdot(vnormalize(vadd(ldir, vneg(p.D))), p.N));
-        d3 specular = vscale(mk(l[6], l[7], l[8]), mat[4] * pow(base, mat[3]));
-        d3 contribution = vadd(diffuse, specular);                       // erl:225-238
-        d3 term = vscale(vcmul(mk(l[0], l[1], l[2]), contribution), 1.0);  // erl:243-247, shadow = 1
+        d3 term = light_term(sc.lights + 9 * (p.phase - 1), mat, p.P, p.N, p.D);
         p.S = vadd(p.S, term);
     }
     p.phase++;
@@ -788,6 +802,8 @@ render_tiled_kernel(const __grid_constant__ DevScene sc, const __grid_constant__
     flush_counters<COUNT>(fp, p.rays, tl);
 }
 
+__device__ void trace_ray_wavefront(const DevScene &sc, d3 O, d3 D, Hit &best);   // ert_wavefront.cuh
+
 // ---- ray batch: nearest_object_intersecting_ray/2 for arbitrary rays (tests, BVH == scan) ----
 template <int ACCEL>
 __global__ void __launch_bounds__(256)
@@ -810,6 +826,10 @@ trace_rays_kernel(const __grid_constant__ DevScene sc, long long n_rays, const d
         float cull = cull_from(f, q.best);
         for (int s = 0; s < sc.n_spheres; s++)
             try_sphere<false>(sc, f, q.O, q.D, __ldg(sc.sph_filter + s), s, -1, q.best, cull, tl);
+    } else if constexpr (ACCEL == 4) {
+        // the traversal of the wavefront kernels (ert_wavefront.cuh)
+        scan_others<false>(sc, q.O, q.D, q.best, -1, tl);
+        if (sc.n_spheres > 0) trace_ray_wavefront(sc, q.O, q.D, q.best);
     } else {
         resolve_free<ACCEL, false>(sc, q, tl);
     }

@@ -116,7 +116,9 @@ typedef struct ert_scene_desc {
 #define ERT_ACCEL_AUTO    0
 #define ERT_ACCEL_EXACT   1   /* FP64 scan of every object, scene read through the constant/L1 path */
 #define ERT_ACCEL_LINEAR  2   /* FP32 conservative filter over shared-memory sphere tiles + FP64 on candidates */
-#define ERT_ACCEL_BVH     3   /* sphere BVH (FP32 conservative slabs/filter) + FP64 on candidates */
+#define ERT_ACCEL_BVH     3   /* sphere BVH (FP32 conservative slabs/filter) + FP64 on candidates;
+                               * wavefront form: path / shadow / shade queues in HBM, full warps of one ray kind */
+#define ERT_ACCEL_BVH_MEGAKERNEL 4  /* same BVH, one launch, per-pixel state machine (kept as a cross-check) */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
 

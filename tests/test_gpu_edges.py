@@ -13,7 +13,7 @@ from helpers import (assert_double_parity, assert_image_parity, oracle_frame,
 from oracle import orc
 
 pytestmark = pytest.mark.gpu
-ACCELS = ("exact", "linear", "bvh")
+ACCELS = ("exact", "linear", "bvh", "bvh_mega")
 CAM = ('camera', ('vector', 0, 0, -2), ('vector', 0, 0, 0), 90, ('screen', 4, 3))
 L1 = ('point_light', ('colour', 1, 1, 0.5), ('vector', 5, -2, 0), ('colour', 1, 1, 1))
 L2 = ('point_light', ('colour', 1, 0, 0.5), ('vector', -10, 0, 7), ('colour', 1, 0, 0.5))

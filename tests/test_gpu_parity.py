@@ -9,7 +9,7 @@ from oracle import orc
 
 pytestmark = pytest.mark.gpu
 
-ACCELS = ("exact", "linear", "bvh")
+ACCELS = ("exact", "linear", "bvh", "bvh_mega")
 
 
 @pytest.fixture(scope="module")
@@ -99,7 +99,7 @@ def test_demo_scene_1080p_depth1(demo):
 
 
 # ---- synthetic 10k-sphere scene (config C3) at oracle-sized resolutions ------------------
-@pytest.mark.parametrize("accel", ("linear", "bvh"))
+@pytest.mark.parametrize("accel", ("linear", "bvh", "bvh_mega"))
 def test_c3_matches_oracle(c3, accel):
     flat, dev = c3
     w, h, depth = 192, 108, 5
@@ -116,8 +116,10 @@ def test_c3_exact_equals_bvh_equals_linear_on_gpu(c3):
     a, _ = dev.render(w, h, depth, fmt="f64", accel="exact")
     b, _ = dev.render(w, h, depth, fmt="f64", accel="bvh")
     c, _ = dev.render(w, h, depth, fmt="f64", accel="linear")
+    d, _ = dev.render(w, h, depth, fmt="f64", accel="bvh_mega")
     assert np.array_equal(a, b)
     assert np.array_equal(a, c)
+    assert np.array_equal(a, d)
 
 
 def test_c3_ray_batch_bvh_equals_linear_scan(c3):
@@ -131,8 +133,10 @@ def test_c3_ray_batch_bvh_equals_linear_scan(c3):
     rays = np.concatenate([o, d], axis=1)
     oe, te = dev.trace_rays(rays, accel="exact")
     ob, tb = dev.trace_rays(rays, accel="bvh")
+    om, tm = dev.trace_rays(rays, accel="bvh_mega")
     ol, tl = dev.trace_rays(rays, accel="linear")
     assert np.array_equal(oe, ob) and np.array_equal(te, tb)
+    assert np.array_equal(oe, om) and np.array_equal(te, tm)
     assert np.array_equal(oe, ol) and np.array_equal(te, tl)
     # and the oracle agrees on a subset
     cam, kind, f = oracle_scene_from_flat(flat)
