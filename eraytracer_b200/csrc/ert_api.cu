@@ -57,6 +57,7 @@ struct HostScene {
     std::vector<float> leaf_filter;    // [n][4]
     Bvh bvh;
     float r_max = 0, pad_c_max = 0, eta_c_max = 0, abs_max = 0;
+    float grid_lo[3] = {0, 0, 0}, grid_scale[3] = {0, 0, 0};
     int n_lights = 0, n_planes = 0, n_tris = 0, n_spheres = 0;
 };
 
@@ -240,6 +241,20 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         if (const char *e = getenv("ERT_BVH_TRAV_COST")) trav_cost = (float)atof(e);
         build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
     }
+    if (h.n_spheres > 0) {
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int64_t k = 0; k < h.n_spheres; k++)
+            for (int a = 0; a < 3; a++) {
+                lo[a] = std::min(lo[a], centers[(size_t)k * 3 + a] - std::fabs(radii[(size_t)k]));
+                hi[a] = std::max(hi[a], centers[(size_t)k * 3 + a] + std::fabs(radii[(size_t)k]));
+            }
+        for (int a = 0; a < 3; a++) {
+            double ext = hi[a] - lo[a];
+            h.grid_lo[a] = (float)lo[a];
+            h.grid_scale[a] = ext > 0 ? (float)((double)(1 << kSortBits) / ext) : 0.f;
+            if (!std::isfinite(h.grid_scale[a]) || !std::isfinite(h.grid_lo[a])) { h.grid_lo[a] = 0; h.grid_scale[a] = 0; }
+        }
+    }
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
@@ -288,6 +303,7 @@ int upload_scene(ert_scene *s)
     UP(h.bvh.nodes, nodes, BvhNode);
 #undef UP
     d.n_nodes = (int)h.bvh.nodes.size();
+    for (int a = 0; a < 3; a++) { d.grid_lo[a] = h.grid_lo[a]; d.grid_scale[a] = h.grid_scale[a]; }
     d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
     for (int i = 0; i < ERT_MAX_SLOTS; i++) {
         Slot &sl = s->slots[i];
@@ -307,9 +323,9 @@ int upload_scene(ert_scene *s)
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, s->device));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, false>, kWfThreads, 0));
         s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, true, false>, kWfThreads, 0));
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
@@ -431,11 +447,13 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
     if (n_pad >= ((size_t)1 << 31)) return fail(ERT_ERR_BADARG, "frame part has more than 2^31 pixels");
     size_t L = (size_t)std::max(s->host.n_lights, 1);
-    // layout: C[3] W[1] q_ray[6] h_geo[9] doubles, then q_pid h_pid h_obj h_order ints, then lit bytes
+    // layout: C[3] W[1] q_ray[6] h_geo[9] r_geo[9] doubles, then q_pid h_pid h_obj h_order r_pid r_obj
+    // r_order r_key ints, then lit bytes, then the sort histogram
     size_t off = 0;
-    size_t o_dbl = off; off += align_up(n_pad * 19 * sizeof(double), 256);
-    size_t o_int = off; off += align_up(n_pad * 4 * sizeof(int), 256);
+    size_t o_dbl = off; off += align_up(n_pad * 28 * sizeof(double), 256);
+    size_t o_int = off; off += align_up(n_pad * 8 * sizeof(int), 256);
     size_t o_lit = off; off += align_up(n_pad * L, 256);
+    size_t o_hist = off; off += align_up(((size_t)kSortCells + kSortBlocks) * sizeof(unsigned int), 256);
     if (sl.wf_cap < off) {
         if (sl.wf_mem) CU(cudaFree(sl.wf_mem));
         sl.wf_mem = nullptr; sl.wf_cap = 0;
@@ -460,7 +478,12 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     wf.tiles_x = tiles_x;
     wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.h_geo = d + 10 * n_pad;
     wf.q_pid = i; wf.h_pid = i + n_pad; wf.h_obj = i + 2 * n_pad; wf.h_order = i + 3 * n_pad;
+    wf.r_geo = d + 19 * n_pad;
+    wf.r_pid = i + 4 * n_pad; wf.r_obj = i + 5 * n_pad; wf.r_order = i + 6 * n_pad;
+    wf.r_key = (unsigned int *)(i + 7 * n_pad);
     wf.lit = base + o_lit;
+    wf.hist = (unsigned int *)(base + o_hist);
+    wf.sums = wf.hist + kSortCells;
     wf.ctr = sl.wf_ctr;
     return ERT_OK;
 }
@@ -478,6 +501,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *la
     uint64_t n = 0;
     // ERT_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
     static const bool debug_sync = getenv("ERT_DEBUG_SYNC") != nullptr;
+    static const bool no_sort = getenv("ERT_WF_NO_SORT") != nullptr;     // A/B switch for the hit binning
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -497,10 +521,24 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *la
             CU(cudaStreamSynchronize(st));
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
-        if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        const bool sort = b >= 1 && d.n_lights > 0 && !no_sort;
+        if (b == 0) {
+            wf_trace_path<true, false, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        } else if (!sort) {
+            wf_trace_path<false, false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        } else {
+            CU(cudaMemsetAsync(wf.hist, 0, (size_t)kSortCells * sizeof(unsigned int), st));
+            wf_trace_path<false, true, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        }
         n++;
         WF_CHECK("wf_trace_path");
+        if (sort) {
+            wf_bin_scan_a<<<kSortBlocks, 1024, 0, st>>>(wf);
+            wf_bin_scan_b<<<1, kSortBlocks, 0, st>>>(wf);
+            wf_bin_scatter<<<s->wf_grid[3], kWfThreads, 0, st>>>(wf, b);
+            n += 3;
+            WF_CHECK("wf_bin_*");
+        }
         if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
         wf_trace_shadow<COUNT><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
         WF_CHECK("wf_trace_shadow");

@@ -54,6 +54,8 @@ struct DevScene {
     float pad_c_max;             // largest centre-rounding pad folded into any R
     float eta_c_max;             // largest centre rounding error bound
     float abs_max;               // largest |coordinate| of any sphere box
+    // uniform grid over the sphere bounds, used only to order the wavefront queues
+    float grid_lo[3], grid_scale[3];
 };
 
 struct FrameParams {

@@ -47,8 +47,20 @@ struct WfBuf {
     int *h_obj, *h_order;       //            object code and list position
     unsigned char *lit;         // [n_lights][n_pad] shadow factor of (light, hit)
     unsigned int *ctr;          // [depth][kWfCtr] queue lengths
+    // hits of bounces >= 1 are binned by location before their shadow rays are traced
+    int *r_pid;                 // unsorted hit queue, same layout as h_*
+    double *r_geo;
+    int *r_obj, *r_order;
+    unsigned int *r_key;        // cell of the hit location (Morton order)
+    unsigned int *hist;         // [kSortCells] cell histogram -> offsets -> scatter cursors
+    unsigned int *sums;         // [kSortBlocks] per-block totals of the histogram scan
 };
 enum WfCtr : int { WF_NHITS = 0, WF_NNEXT = 1, kWfCtr = 4 };
+constexpr int kWfThreads = 256;
+constexpr int kSortBits = 7;                                  // per axis
+constexpr int kSortCells = 1 << (3 * kSortBits);              // 2 Mi cells over the sphere bounds
+constexpr int kSortScanBlock = 4096;                          // cells scanned by one block
+constexpr int kSortBlocks = kSortCells / kSortScanBlock;      // 512
 
 // ------------------------------------------------------------------ slim ray for the traversal
 // Same bounds as FRay (DESIGN.md "Filter bounds"); the slab constants are written so that the
@@ -229,11 +241,107 @@ __device__ __forceinline__ void wf_flush(const FrameParams &fp, unsigned int ray
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
+// ------------------------------------------------------------------ binning hits by location
+// Rays that leave a curved surface scatter: the hits of bounce >= 1 arrive in an order that
+// has little to do with where they are, and a warp of their shadow rays walks 32 unrelated
+// parts of the tree.  A counting sort by the Morton cell of the hit location (a uniform grid
+// over the sphere bounds) restores the coherence bounce 0 has for free.  The order of a queue
+// never changes a pixel (every record carries its pixel), so this is purely a schedule.
+__device__ __forceinline__ unsigned int part1by2(unsigned int x)
+{
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x30000ffu;
+    x = (x | (x << 8)) & 0x300f00fu;
+    x = (x | (x << 4)) & 0x30c30c3u;
+    x = (x | (x << 2)) & 0x9249249u;
+    return x;
+}
+__device__ __forceinline__ unsigned int sort_cell(const DevScene &sc, d3 P)
+{
+    const float top = (float)((1 << kSortBits) - 1);
+    float fx = fminf(fmaxf(((float)P.x - sc.grid_lo[0]) * sc.grid_scale[0], 0.f), top);
+    float fy = fminf(fmaxf(((float)P.y - sc.grid_lo[1]) * sc.grid_scale[1], 0.f), top);
+    float fz = fminf(fmaxf(((float)P.z - sc.grid_lo[2]) * sc.grid_scale[2], 0.f), top);
+    return part1by2((unsigned int)fx) | (part1by2((unsigned int)fy) << 1) | (part1by2((unsigned int)fz) << 2);
+}
+
+// exclusive scan of the histogram, phase A: each block scans kSortScanBlock cells in place
+__global__ void __launch_bounds__(1024) wf_bin_scan_a(const __grid_constant__ WfBuf wf)
+{
+    __shared__ unsigned int warp_sums[32];
+    unsigned int *h = wf.hist + (size_t)blockIdx.x * kSortScanBlock + threadIdx.x * 4;
+    uint4 v = *reinterpret_cast<uint4 *>(h);
+    unsigned int t = v.x + v.y + v.z + v.w;
+    unsigned int incl = t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_sums[lane] = wi - w;
+        if (lane == 31) wf.sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    unsigned int base = warp_sums[warp] + incl - t;
+    uint4 o;
+    o.x = base; o.y = base + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+    *reinterpret_cast<uint4 *>(h) = o;
+}
+// phase B: exclusive scan of the kSortBlocks block totals (one block)
+__global__ void __launch_bounds__(kSortBlocks) wf_bin_scan_b(const __grid_constant__ WfBuf wf)
+{
+    __shared__ unsigned int warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int t = wf.sums[threadIdx.x], incl = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = lane < kSortBlocks / 32 ? warp_sums[lane] : 0u, wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    wf.sums[threadIdx.x] = warp_sums[warp] + incl - t;
+}
+// scatter: every unsorted hit record moves to its cell's range of the sorted hit queue
+__global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_constant__ WfBuf wf, int bounce)
+{
+    const unsigned int n_hits = wf.ctr[bounce * kWfCtr + WF_NHITS];
+    const size_t np = (size_t)wf.n_pad;
+    for (size_t h = (size_t)blockIdx.x * kWfThreads + threadIdx.x; h < n_hits; h += (size_t)gridDim.x * kWfThreads) {
+        unsigned int key = wf.r_key[h];
+        size_t s = (size_t)atomicAdd(wf.hist + key, 1u) + wf.sums[key / kSortScanBlock];
+        wf.h_pid[s] = wf.r_pid[h];
+        wf.h_obj[s] = wf.r_obj[h];
+        wf.h_order[s] = wf.r_order[h];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wf.h_geo[k * np + s] = wf.r_geo[k * np + h];
+    }
+}
+
 // ------------------------------------------------------------------ kernels
-constexpr int kWfThreads = 256;
 
 // Path rays of one bounce.  FIRST: rays are generated from the pixel index (erl:486-511).
-template <bool FIRST, bool COUNT>
+template <bool FIRST, bool SORT, bool COUNT>
 __global__ void __launch_bounds__(kWfThreads)
 wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
               const __grid_constant__ WfBuf wf, int bounce)
@@ -284,10 +392,15 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                 size_t s = slot0 + __popc(m & ((1u << lane) - 1u));
                 d3 P = vadd(O, vscale(D, best.t));            // erl:384-387 / 443-447 / 471-475
                 d3 N = hit_normal(sc, best.obj, P);
-                wf.h_pid[s] = pid;
-                wf.h_obj[s] = best.obj;
-                wf.h_order[s] = best.order;
-                double *g = wf.h_geo + s;
+                (SORT ? wf.r_pid : wf.h_pid)[s] = pid;
+                (SORT ? wf.r_obj : wf.h_obj)[s] = best.obj;
+                (SORT ? wf.r_order : wf.h_order)[s] = best.order;
+                if constexpr (SORT) {
+                    unsigned int key = sort_cell(sc, P);
+                    wf.r_key[s] = key;
+                    atomicAdd(wf.hist + key, 1u);
+                }
+                double *g = (SORT ? wf.r_geo : wf.h_geo) + s;
                 g[0] = P.x; g[np] = P.y; g[2 * np] = P.z;
                 g[3 * np] = N.x; g[4 * np] = N.y; g[5 * np] = N.z;
                 g[6 * np] = D.x; g[7 * np] = D.y; g[8 * np] = D.z;
