@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libert_b200.so")
+# ERT_B200_LIB selects another build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("ERT_B200_LIB") or os.path.join(HERE, "lib", "libert_b200.so")
 
 ERT_OK, ERT_ERR_BADARG, ERT_ERR_NO_DEVICE, ERT_ERR_CUDA, ERT_ERR_NOMEM = 0, 1, 2, 3, 4
 FMT_RGB8, FMT_F32, FMT_F64 = 0, 1, 2

@@ -323,9 +323,9 @@ int upload_scene(ert_scene *s)
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, s->device));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false>, kWfThreads, 0));
         s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, true, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false>, kWfThreads, 0));
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
@@ -447,11 +447,12 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
     if (n_pad >= ((size_t)1 << 31)) return fail(ERT_ERR_BADARG, "frame part has more than 2^31 pixels");
     size_t L = (size_t)std::max(s->host.n_lights, 1);
-    // layout: C[3] W[1] q_ray[6] h_geo[9] r_geo[9] doubles, then q_pid h_pid h_obj h_order r_pid r_obj
-    // r_order r_key ints, then lit bytes, then the sort histogram
+    // layout: C[3] W[1] q_ray[6] res_t[1] doubles | hits, raw_hits records | q_pid res_hit[2] r_key ints |
+    // lit bytes | sort histogram + block sums
     size_t off = 0;
-    size_t o_dbl = off; off += align_up(n_pad * 28 * sizeof(double), 256);
-    size_t o_int = off; off += align_up(n_pad * 8 * sizeof(int), 256);
+    size_t o_dbl = off; off += align_up(n_pad * 11 * sizeof(double), 256);
+    size_t o_rec = off; off += align_up(n_pad * 2 * sizeof(HitRec), 256);
+    size_t o_int = off; off += align_up(n_pad * 4 * sizeof(int), 256);
     size_t o_lit = off; off += align_up(n_pad * L, 256);
     size_t o_hist = off; off += align_up(((size_t)kSortCells + kSortBlocks) * sizeof(unsigned int), 256);
     if (sl.wf_cap < off) {
@@ -476,11 +477,9 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     int *i = (int *)(base + o_int);
     wf.n_pad = (int)n_pad;
     wf.tiles_x = tiles_x;
-    wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.h_geo = d + 10 * n_pad;
-    wf.q_pid = i; wf.h_pid = i + n_pad; wf.h_obj = i + 2 * n_pad; wf.h_order = i + 3 * n_pad;
-    wf.r_geo = d + 19 * n_pad;
-    wf.r_pid = i + 4 * n_pad; wf.r_obj = i + 5 * n_pad; wf.r_order = i + 6 * n_pad;
-    wf.r_key = (unsigned int *)(i + 7 * n_pad);
+    wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.res_t = d + 10 * n_pad;
+    wf.hits = (HitRec *)(base + o_rec); wf.raw_hits = wf.hits + n_pad;
+    wf.q_pid = i; wf.res_hit = (int2 *)(i + n_pad); wf.r_key = (unsigned int *)(i + 3 * n_pad);
     wf.lit = base + o_lit;
     wf.hist = (unsigned int *)(base + o_hist);
     wf.sums = wf.hist + kSortCells;
@@ -521,25 +520,26 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *la
             CU(cudaStreamSynchronize(st));
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
-        const bool sort = b >= 1 && d.n_lights > 0 && !no_sort;
-        if (b == 0) {
-            wf_trace_path<true, false, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        } else if (!sort) {
-            wf_trace_path<false, false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        } else {
-            CU(cudaMemsetAsync(wf.hist, 0, (size_t)kSortCells * sizeof(unsigned int), st));
-            wf_trace_path<false, true, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        }
+        const bool sort = b >= 1 && !no_sort;
+        if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         n++;
         WF_CHECK("wf_trace_path");
-        if (sort) {
+        if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
+        if (b == 0) {
+            wf_emit_hits<true, false><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
+        } else if (!sort) {
+            wf_emit_hits<false, false><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
+        } else {
+            CU(cudaMemsetAsync(wf.hist, 0, (size_t)kSortCells * sizeof(unsigned int), st));
+            wf_emit_hits<false, true><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
             wf_bin_scan_a<<<kSortBlocks, 1024, 0, st>>>(wf);
             wf_bin_scan_b<<<1, kSortBlocks, 0, st>>>(wf);
             wf_bin_scatter<<<s->wf_grid[3], kWfThreads, 0, st>>>(wf, b);
             n += 3;
-            WF_CHECK("wf_bin_*");
         }
-        if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
+        n++;
+        WF_CHECK("wf_emit_hits / wf_bin_*");
         wf_trace_shadow<COUNT><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
         WF_CHECK("wf_trace_shadow");
         wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);

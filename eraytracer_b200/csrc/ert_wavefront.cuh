@@ -35,6 +35,18 @@
 
 namespace ert {
 
+// One hit of a path ray.  96 bytes, laid out so that each consumer touches whole 32-byte
+// sectors: the shadow stage needs only the first one.
+struct alignas(16) HitRec {
+    double P[3];                // hit location
+    int obj, order;             // object code, list position
+    double N[3];                // normal
+    int pid, pad0;              // pixel of the path
+    double D[3];                // direction of the ray that hit
+    double pad1;
+};
+static_assert(sizeof(HitRec) == 96, "HitRec must be 96 bytes");
+
 struct WfBuf {
     int n_pad;                  // pixels of this part padded to whole 8x4 tiles: tiles * 32
     int tiles_x;                // tiles per row of tiles
@@ -42,26 +54,28 @@ struct WfBuf {
     double *W;                  // [n_pad]    product of (lights * reflectivity) of earlier bounces
     int *q_pid;                 // path queue: pixel of each ray
     double *q_ray;              // [6][n_pad] origin xyz, direction xyz
-    int *h_pid;                 // hit queue: pixel,
-    double *h_geo;              // [9][n_pad] hit location, normal, incoming direction
-    int *h_obj, *h_order;       //            object code and list position
+    double *res_t;              // nearest hit of each path ray: Distance,
+    int2 *res_hit;              //   (object code or -1, list position)
+    HitRec *hits;               // hit queue the shadow and shade stages read
+    HitRec *raw_hits;           // hit queue in arrival order (bounces >= 1, before binning)
+    unsigned int *r_key;        // cell of each raw hit (Morton order)
     unsigned char *lit;         // [n_lights][n_pad] shadow factor of (light, hit)
-    unsigned int *ctr;          // [depth][kWfCtr] queue lengths
-    // hits of bounces >= 1 are binned by location before their shadow rays are traced
-    int *r_pid;                 // unsorted hit queue, same layout as h_*
-    double *r_geo;
-    int *r_obj, *r_order;
-    unsigned int *r_key;        // cell of the hit location (Morton order)
+    unsigned int *ctr;          // [depth][kWfCtr] queue lengths and work cursors
     unsigned int *hist;         // [kSortCells] cell histogram -> offsets -> scatter cursors
     unsigned int *sums;         // [kSortBlocks] per-block totals of the histogram scan
 };
-enum WfCtr : int { WF_NHITS = 0, WF_NNEXT = 1, kWfCtr = 4 };
+enum WfCtr : int { WF_NHITS = 0, WF_NNEXT = 1, WF_FETCH_PATH = 2 /* 64-bit */, WF_FETCH_SHADOW = 4 /* 64-bit */, kWfCtr = 8 };
 constexpr int kWfThreads = 256;
+#ifndef ERT_WF_LDG256
+#define ERT_WF_LDG256 1             /* 64-byte BVH nodes fetched as two 256-bit loads */
+#endif
+#ifndef ERT_WF_MINBLOCKS
+#define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
+#endif
 constexpr int kSortBits = 7;                                  // per axis
 constexpr int kSortCells = 1 << (3 * kSortBits);              // 2 Mi cells over the sphere bounds
 constexpr int kSortScanBlock = 4096;                          // cells scanned by one block
 constexpr int kSortBlocks = kSortCells / kSortScanBlock;      // 512
-
 // ------------------------------------------------------------------ slim ray for the traversal
 // Same bounds as FRay (DESIGN.md "Filter bounds"); the slab constants are written so that the
 // near/far choice needs no select: with m the absolute margin,
@@ -74,15 +88,35 @@ struct SRay {
     float klx, kly, klz;
     float khx, khy, khz;
     float theta, bcull, pad2, m4;
-    double inv_sqrt_a, a;
 };
+// The FP64 ray (origin, direction, a = D.D, 1/sqrt(a)) is needed only by the rare literal tests:
+// it lives in shared memory, one column per thread, so the walk keeps it out of registers.
+struct RaySlot {
+    double *p;                                           // &slots[0][threadIdx.x], stride kWfThreads
+    __device__ __forceinline__ double get(int k) const { return p[k * kWfThreads]; }
+    __device__ __forceinline__ void put(d3 O, d3 D, double a, double inv)
+    {
+        p[0] = O.x; p[kWfThreads] = O.y; p[2 * kWfThreads] = O.z;
+        p[3 * kWfThreads] = D.x; p[4 * kWfThreads] = D.y; p[5 * kWfThreads] = D.z;
+        p[6 * kWfThreads] = a; p[7 * kWfThreads] = inv;
+    }
+    __device__ __forceinline__ d3 O() const { return mk(get(0), get(1), get(2)); }
+    __device__ __forceinline__ d3 D() const { return mk(get(3), get(4), get(5)); }
+    __device__ __forceinline__ double a() const { return get(6); }
+    __device__ __forceinline__ double inv_sqrt_a() const { return get(7); }
+};
+constexpr int kRaySlotDoubles = 8;
 #define ERT_KAPPA 1.00006103515625f   /* 1 + 2^-14 >= (1+2^-16)/(1-2^-16): slab slack as one factor */
 
-__device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &f)
+__device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &f, double &a_out, double &inv_out)
 {
-    f.a = D.x * D.x + D.y * D.y + D.z * D.z;
-    double inv = 1.0 / sqrt(f.a);
-    f.inv_sqrt_a = inv;
+    const double a = D.x * D.x + D.y * D.y + D.z * D.z;
+    // 1/sqrt(a): directions are unit vectors up to rounding except after a bounce off an
+    // un-normalised plane normal; 1.5 - a/2 is 1/sqrt(a) to 4e-19 relative for |a-1| <= 1e-9
+    // (this value only scales the FP32 filter ray and the cull distance, both with 2^-16 slack)
+    double inv = (fabs(a - 1.0) <= 1e-9) ? (1.5 - 0.5 * a) : 1.0 / sqrt(a);
+    a_out = a;
+    inv_out = inv;
     f.ox = (float)O.x; f.oy = (float)O.y; f.oz = (float)O.z;
     double k = inv * ERT_KD;
     f.dx = (float)(D.x * k); f.dy = (float)(D.y * k); f.dz = (float)(D.z * k);
@@ -95,9 +129,18 @@ __device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &
     float oabs = fmaxf(fmaxf(fabsf(f.ox), fabsf(f.oy)), fabsf(f.oz));
     float m = eo + 32.0f * ERT_U * (oabs + sc.abs_max);
     f.m4 = 4.0f * m;
-    f.ix = 1.0f / clamp_dir(f.dx); f.iy = 1.0f / clamp_dir(f.dy); f.iz = 1.0f / clamp_dir(f.dz);
+    // approximate reciprocals (2 ulp): a relative error of the slope scales every slab distance
+    // of that axis alike and is covered by kappa and the 2^-16 slack of the cull distance
+    f.ix = __frcp_rn(clamp_dir(f.dx)); f.iy = __frcp_rn(clamp_dir(f.dy)); f.iz = __frcp_rn(clamp_dir(f.dz));
     f.klx = -(f.ox + m) * f.ix; f.kly = -(f.oy + m) * f.iy; f.klz = -(f.oz + m) * f.iz;
     f.khx = -(f.ox - m) * f.ix; f.khy = -(f.oy - m) * f.iy; f.khz = -(f.oz - m) * f.iz;
+}
+
+__device__ __forceinline__ void ldg256(const void *p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
 }
 
 // 6 FFMA + 6 FMNMX + 2 FMNMX3 + FMNMX + FMUL + FMNMX + compare.  `cullk` already carries kappa.
@@ -113,15 +156,17 @@ __device__ __forceinline__ bool slab_test(const SRay &f, float lox, float hix, f
     return tnear <= fminf(tf * ERT_KAPPA, cullk);
 }
 
-template <class R>
-__device__ __forceinline__ float cullk_from(const R &f, const Hit &best)
+// reference Distance of the incumbent -> filter-space cull distance (upper bound), kappa included
+__device__ __forceinline__ float cullk_from(const SRay &f, double inv_sqrt_a, const Hit &best)
 {
-    return cull_from(f, best) * ERT_KAPPA;
+    if (best.obj < 0) return __int_as_float(0x7f800000);
+    float sf = __double2float_ru(best.t * inv_sqrt_a);
+    return (sf + fabsf(sf) * ERT_REL16 + f.m4) * ERT_KAPPA;
 }
 
 // One leaf sphere: FP32 filter, then the literal FP64 test on survivors (rare).
 template <bool COUNT>
-__device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, d3 O, d3 D, float4 fs, int slot,
+__device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, const RaySlot &ray, float4 fs, int slot,
                                             int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
 {
     float b, v;
@@ -133,88 +178,129 @@ __device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, d
     if (code == skip_obj) return;
     double t;
     TALLY(exact_sph);
-    if (sphere_exact(O, D, f.a, sc.sph_exact[sph], t)) {
+    if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
         int ord = sc.sph_order[sph];
         if (better(t, ord, best)) {
             best.t = t; best.order = ord; best.obj = code;
-            cullk = cullk_from(f, best);
+            cullk = cullk_from(f, ray.inv_sqrt_a(), best);
         }
     }
 }
 
-// While-while traversal: all lanes walk inner nodes until each holds a leaf (or is done), then
-// the leaves are processed together.  ANY: stop at the first improvement of the incumbent.
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void traverse_bvh(const DevScene &sc, d3 O, d3 D, const SRay &f, Hit &best, int skip_obj,
-                                             int seed_obj, Tally<COUNT> &tl)
-{
-    constexpr int SENT = INT_MIN;
+// ------------------------------------------------------------------ resumable traversal
+// The state of one ray's walk.  trav_step() runs inner nodes until the ray holds a leaf,
+// processes that leaf and pops (while-while: the lanes of a warp meet again at every leaf).
+// Handing new rays to finished lanes in mid-walk (persistent lanes with dynamic fetch) was
+// measured and lost: the set-up of a few lanes at a time costs more than the idle lanes do.
+// ANY: the search ends at the first improvement of the incumbent (shadow rays).
+constexpr int kTravDone = INT_MIN;
+template <bool ANY>
+struct Trav {
+    int node, sp;
+    float cullk;
     int stack[kBvhStack];
-    float tstack[ANY ? 1 : kBvhStack];
-    int sp = 0;
-    stack[0] = SENT;
+    float tstack[ANY ? 1 : kBvhStack];    // entry distance of each pushed subtree (closest-hit only)
+};
+
+template <bool ANY>
+__device__ __forceinline__ void trav_start(Trav<ANY> &tr, const SRay &f, double inv_sqrt_a, const Hit &best)
+{
+    tr.stack[0] = kTravDone;
     // -inf: a triangle incumbent can have t < 0 (erl:402-455 has no t >= 0 test), so cullk may be negative
-    if constexpr (!ANY) tstack[0] = __int_as_float(0xff800000);
-    sp = 1;
-    int node = 0;
-    float cullk = cullk_from(f, best);
-    for (;;) {
-        while (node >= 0) {
-            WF_ASSERT(node < sc.n_nodes, "node %d of %d sp %d", node, sc.n_nodes, sp);
-            const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
-            float4 a0 = __ldg(np), a1 = __ldg(np + 1), a2 = __ldg(np + 2);
-            int2 ch = __ldg(reinterpret_cast<const int2 *>(np + 3));
-            float tn0, tn1;
-            if constexpr (COUNT) tl.box += 2;
-            bool h0 = slab_test(f, a0.x, a0.y, a0.z, a0.w, a2.x, a2.y, cullk, tn0);
-            bool h1 = slab_test(f, a1.x, a1.y, a1.z, a1.w, a2.z, a2.w, cullk, tn1);
-            if (h0 && h1) {
-                bool swap = tn1 < tn0;
-                node = swap ? ch.y : ch.x;
-                if (sp < kBvhStack) {
-                    stack[sp] = swap ? ch.x : ch.y;
-                    if constexpr (!ANY) tstack[sp] = swap ? tn0 : tn1;
-                    sp++;
-                }
-            } else if (h0) {
-                node = ch.x;
-            } else if (h1) {
-                node = ch.y;
-            } else {
-                if constexpr (ANY) {
-                    node = stack[--sp];
-                } else {
-                    do { --sp; WF_ASSERT(sp >= 0, "sp %d cullk %g", sp, cullk); node = stack[sp]; } while (tstack[sp] > cullk);
-                }
-            }
-            WF_ASSERT(sp >= 0 && sp <= kBvhStack, "sp %d", sp);
-        }
-        if (node == SENT) break;
-        {
-            int code = ~node;
-            int first = code >> 3, cnt = (code & 7) + 1;
-            WF_ASSERT(first >= 0 && first + cnt <= sc.n_spheres, "leaf first %d cnt %d node %d sp %d", first, cnt, node, sp);
-#pragma unroll 1
-            for (int k = 0; k < cnt; k++) {
-                float4 fs = __ldg(sc.leaf_filter + first + k);
-                leaf_sphere<COUNT>(sc, f, O, D, fs, first + k, skip_obj, best, cullk, tl);
-            }
-        }
-        if constexpr (ANY) {
-            if (best.obj != seed_obj) break;
-            node = stack[--sp];
-        } else {
-            do { --sp; WF_ASSERT(sp >= 0, "sp %d cullk %g (leaf)", sp, cullk); node = stack[sp]; } while (tstack[sp] > cullk);
-        }
+    if constexpr (!ANY) tr.tstack[0] = __int_as_float(0xff800000);
+    tr.sp = 1;
+    tr.node = 0;
+    tr.cullk = cullk_from(f, inv_sqrt_a, best);
+}
+
+template <bool ANY>
+__device__ __forceinline__ void trav_pop(Trav<ANY> &tr)
+{
+    if constexpr (ANY) {
+        tr.node = tr.stack[--tr.sp];
+    } else {
+        do {
+            --tr.sp;
+            WF_ASSERT(tr.sp >= 0, "sp %d cullk %g", tr.sp, tr.cullk);
+            tr.node = tr.stack[tr.sp];
+        } while (tr.tstack[tr.sp] > tr.cullk);
     }
 }
 
+// returns true when the search is over
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool trav_step(Trav<ANY> &tr, const DevScene &sc, const RaySlot &ray, const SRay &f,
+                                          Hit &best, int skip_obj, int seed_obj, Tally<COUNT> &tl)
+{
+    while (tr.node >= 0) {
+        WF_ASSERT(tr.node < sc.n_nodes, "node %d of %d sp %d", tr.node, sc.n_nodes, tr.sp);
+        // one 64-byte node = two 256-bit loads (LDG.E.256): half the L1 wavefronts of four 128-bit ones
+        float n0[8], n1[8];
+#if ERT_WF_LDG256
+        ldg256(sc.nodes + tr.node, n0);
+        ldg256(reinterpret_cast<const char *>(sc.nodes + tr.node) + 32, n1);
+#else
+        {
+            const float4 *np4 = reinterpret_cast<const float4 *>(sc.nodes + tr.node);
+            float4 q0 = __ldg(np4), q1 = __ldg(np4 + 1), q2 = __ldg(np4 + 2);
+            float2 q3 = __ldg(reinterpret_cast<const float2 *>(np4 + 3));
+            n0[0] = q0.x; n0[1] = q0.y; n0[2] = q0.z; n0[3] = q0.w; n0[4] = q1.x; n0[5] = q1.y; n0[6] = q1.z; n0[7] = q1.w;
+            n1[0] = q2.x; n1[1] = q2.y; n1[2] = q2.z; n1[3] = q2.w; n1[4] = q3.x; n1[5] = q3.y; n1[6] = 0.f; n1[7] = 0.f;
+        }
+#endif
+        int2 ch = make_int2(__float_as_int(n1[4]), __float_as_int(n1[5]));
+        float tn0, tn1;
+        if constexpr (COUNT) tl.box += 2;
+        bool h0 = slab_test(f, n0[0], n0[1], n0[2], n0[3], n1[0], n1[1], tr.cullk, tn0);
+        bool h1 = slab_test(f, n0[4], n0[5], n0[6], n0[7], n1[2], n1[3], tr.cullk, tn1);
+        if (h0 && h1) {
+            bool swap = tn1 < tn0;
+            tr.node = swap ? ch.y : ch.x;
+            if (tr.sp < kBvhStack) {
+                tr.stack[tr.sp] = swap ? ch.x : ch.y;
+                if constexpr (!ANY) tr.tstack[tr.sp] = swap ? tn0 : tn1;
+                tr.sp++;
+            }
+        } else if (h0) {
+            tr.node = ch.x;
+        } else if (h1) {
+            tr.node = ch.y;
+        } else {
+            trav_pop(tr);
+        }
+    }
+    if (tr.node == kTravDone) return true;
+    {
+        int code = ~tr.node;
+        int first = code >> 3, cnt = (code & 7) + 1;
+        WF_ASSERT(first >= 0 && first + cnt <= sc.n_spheres, "leaf first %d cnt %d", first, cnt);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            float4 fs = __ldg(sc.leaf_filter + first + k);
+            leaf_sphere<COUNT>(sc, f, ray, fs, first + k, skip_obj, best, tr.cullk, tl);
+        }
+    }
+    if constexpr (ANY) {
+        if (best.obj != seed_obj) return true;
+    }
+    trav_pop(tr);
+    return tr.node == kTravDone;
+}
+
+// one ray, no persistence (ert_trace_rays); the FP64 ray sits in a local column
 __device__ void trace_ray_wavefront(const DevScene &sc, d3 O, d3 D, Hit &best)
 {
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
     SRay f;
     Tally<false> tl;
-    make_sray(sc, O, D, f);
-    traverse_bvh<false, false>(sc, O, D, f, best, -1, -1, tl);
+    Trav<false> tr;
+    double a, inv;
+    make_sray(sc, O, D, f, a, inv);
+    ray.put(O, D, a, inv);
+    trav_start(tr, f, inv, best);
+    while (!trav_step<false, false>(tr, sc, ray, f, best, -1, -1, tl)) { }
 }
 
 // ------------------------------------------------------------------ pixel <-> queue index
@@ -235,10 +321,21 @@ __device__ __forceinline__ void pixel_of_index(const FrameParams &fp, const WfBu
     inside = X < fp.width && local_y < fp.local_rows && Y < fp.height;
 }
 
-template <bool COUNT>
-__device__ __forceinline__ void wf_flush(const FrameParams &fp, unsigned int rays, const Tally<COUNT> &tl)
+__device__ __forceinline__ void path_ray_of_index(const FrameParams &fp, const WfBuf &wf, bool first, unsigned int i,
+                                                  d3 &O, d3 &D, int &pid, bool &valid)
 {
-    flush_counters<COUNT>(fp, (int)rays, tl);
+    if (first) {
+        int X, ly, Y;
+        pixel_of_index(fp, wf, (int)i, X, ly, Y, valid);
+        pid = (int)i;
+        if (valid) primary_ray(fp, X, Y, O, D);                 // erl:486-511
+    } else {
+        const size_t np = (size_t)wf.n_pad;
+        valid = true;
+        pid = wf.q_pid[i];
+        O = mk(wf.q_ray[i], wf.q_ray[np + i], wf.q_ray[2 * np + i]);
+        D = mk(wf.q_ray[3 * np + i], wf.q_ray[4 * np + i], wf.q_ray[5 * np + i]);
+    }
 }
 
 // ------------------------------------------------------------------ binning hits by location
@@ -322,140 +419,238 @@ __global__ void __launch_bounds__(kSortBlocks) wf_bin_scan_b(const __grid_consta
     __syncthreads();
     wf.sums[threadIdx.x] = warp_sums[warp] + incl - t;
 }
-// scatter: every unsorted hit record moves to its cell's range of the sorted hit queue
+// scatter: every raw hit record moves to its cell's range of the sorted hit queue
 __global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_constant__ WfBuf wf, int bounce)
 {
     const unsigned int n_hits = wf.ctr[bounce * kWfCtr + WF_NHITS];
-    const size_t np = (size_t)wf.n_pad;
     for (size_t h = (size_t)blockIdx.x * kWfThreads + threadIdx.x; h < n_hits; h += (size_t)gridDim.x * kWfThreads) {
         unsigned int key = wf.r_key[h];
         size_t s = (size_t)atomicAdd(wf.hist + key, 1u) + wf.sums[key / kSortScanBlock];
-        wf.h_pid[s] = wf.r_pid[h];
-        wf.h_obj[s] = wf.r_obj[h];
-        wf.h_order[s] = wf.r_order[h];
-#pragma unroll
-        for (int k = 0; k < 9; k++) wf.h_geo[k * np + s] = wf.r_geo[k * np + h];
+        const uint4 *src = reinterpret_cast<const uint4 *>(wf.raw_hits + h);
+        uint4 *dst = reinterpret_cast<uint4 *>(wf.hits + s);
+        uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3], r4 = src[4], r5 = src[5];
+        dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3; dst[4] = r4; dst[5] = r5;
     }
 }
 
 // ------------------------------------------------------------------ kernels
+// lanes below `lane` in mask m
+__device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc(m & ((1u << lane) - 1u)); }
 
-// Path rays of one bounce.  FIRST: rays are generated from the pixel index (erl:486-511).
-template <bool FIRST, bool SORT, bool COUNT>
-__global__ void __launch_bounds__(kWfThreads)
+// Work distribution of the traversal kernels.  A warp owns a chunk of kWfChunk consecutive
+// queue entries at a time (one atomic per chunk) and works through it in batches of 32, so the
+// rays a lane sees one after another are 32 entries apart in the (binned) queue: neighbours in
+// space.  That is what makes the previous ray's sphere a good first guess for the next one.
+#ifndef ERT_WF_CHUNK
+#define ERT_WF_CHUNK 128
+#endif
+constexpr unsigned int kWfChunk = ERT_WF_CHUNK;
+static_assert(kWfChunk % 32 == 0, "chunks are whole batches");
+
+__device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned long long total, int lane,
+                                           unsigned long long &begin, unsigned long long &end)
+{
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kWfChunk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) return false;
+    begin = base;
+    end = base + kWfChunk < total ? base + kWfChunk : total;
+    return true;
+}
+
+// Path rays of one bounce: nearest_object_intersecting_ray/2 (erl:300-346) for every ray of
+// the path queue (FIRST: for every pixel, rays generated on the fly).
+template <bool FIRST, bool COUNT>
+__global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
 wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
               const __grid_constant__ WfBuf wf, int bounce)
+{
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned long long n = FIRST ? (unsigned long long)wf.n_pad
+                                       : (unsigned long long)wf.ctr[(bounce - 1) * kWfCtr + WF_NNEXT];
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_PATH);
+    const int lane = threadIdx.x & 31;
+    Tally<COUNT> tl;
+    unsigned int rays = 0;
+    int hint = -1;                                   // sphere hit by this lane's previous ray
+    unsigned long long begin, end;
+    while (next_chunk(cursor, n, lane, begin, end)) {
+        for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
+            const unsigned long long i64 = b0 + lane;
+            if (i64 >= end) continue;
+            const unsigned int i = (unsigned int)i64;
+            bool valid;
+            int pid;
+            Hit best;
+            best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+            {
+                d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
+                path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
+                if (valid) {
+                    rays++;
+                    scan_others<COUNT>(sc, O, D, best, -1, tl);
+                    if (sc.n_spheres > 0) {
+                        SRay f;
+                        double a, inv;
+                        make_sray(sc, O, D, f, a, inv);
+                        ray.put(O, D, a, inv);
+                        int skip = -1;
+                        if (hint >= 0) {
+                            // seed the search with the previous ray's sphere: a real candidate of the
+                            // scan, so the minimum over (t, order) is unchanged
+                            double t;
+                            TALLY(exact_sph);
+                            if (sphere_exact(O, D, a, sc.sph_exact[hint], t)) {
+                                int ord = sc.sph_order[hint];
+                                if (better(t, ord, best)) {
+                                    best.t = t; best.order = ord; best.obj = obj_code(OBJ_SPHERE, hint);
+                                    skip = best.obj;
+                                }
+                            }
+                        }
+                        Trav<false> tr;
+                        trav_start(tr, f, inv, best);
+                        while (!trav_step<false, COUNT>(tr, sc, ray, f, best, skip, -1, tl)) { }
+                        if (best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
+                    }
+                }
+            }
+            wf.res_hit[i] = make_int2(valid ? best.obj : -1, best.order);
+            wf.res_t[i] = best.t;
+        }
+    }
+    flush_counters<COUNT>(fp, (int)rays, tl);
+}
+
+// Turns the nearest-hit results of one bounce into the hit queue: hit location and normal
+// (erl:384-390, 443-451, 471-476), compaction, and (SORT) the cell histogram for the binning.
+template <bool FIRST, bool SORT>
+__global__ void __launch_bounds__(kWfThreads)
+wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
+             const __grid_constant__ WfBuf wf, int bounce)
 {
     unsigned int *ctr = wf.ctr + bounce * kWfCtr;
     const unsigned int n = FIRST ? (unsigned int)wf.n_pad : wf.ctr[(bounce - 1) * kWfCtr + WF_NNEXT];
     const int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * kWfThreads + threadIdx.x) >> 5;
     const unsigned int n_warps = (gridDim.x * kWfThreads) >> 5;
-    const size_t np = (size_t)wf.n_pad;
-    Tally<COUNT> tl;
-    unsigned int rays = 0;
+    HitRec *out = SORT ? wf.raw_hits : wf.hits;
     for (unsigned long long base = (unsigned long long)warp * 32; base < n; base += (unsigned long long)n_warps * 32) {
         unsigned int i = (unsigned int)base + lane;
-        bool valid = i < n;
-        d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
-        int pid = 0;
-        if constexpr (FIRST) {
-            int X, ly, Y;
-            pixel_of_index(fp, wf, (int)i, X, ly, Y, valid);
-            pid = (int)i;
-            if (valid) primary_ray(fp, X, Y, O, D);
-        } else if (valid) {
-            WF_ASSERT(i < (unsigned)wf.n_pad, "queue index %u of %d", i, wf.n_pad);
-            pid = wf.q_pid[i];
-            O = mk(wf.q_ray[i], wf.q_ray[np + i], wf.q_ray[2 * np + i]);
-            D = mk(wf.q_ray[3 * np + i], wf.q_ray[4 * np + i], wf.q_ray[5 * np + i]);
-        }
-        Hit best;
-        best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
-        if (valid) {
-            rays++;
-            scan_others<COUNT>(sc, O, D, best, -1, tl);
-            if (sc.n_spheres > 0) {
-                SRay f;
-                make_sray(sc, O, D, f);
-                traverse_bvh<false, COUNT>(sc, O, D, f, best, -1, -1, tl);
-            }
-        }
-        bool hit = valid && best.obj >= 0;
+        int2 r = make_int2(-1, 0);
+        if (i < n) r = wf.res_hit[i];
+        bool hit = r.x >= 0;
         unsigned int m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            int leader = __ffs(m) - 1;
-            unsigned int slot0 = 0;
-            if (lane == leader) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)__popc(m));
-            slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-            if (hit) {
-                size_t s = slot0 + __popc(m & ((1u << lane) - 1u));
-                d3 P = vadd(O, vscale(D, best.t));            // erl:384-387 / 443-447 / 471-475
-                d3 N = hit_normal(sc, best.obj, P);
-                (SORT ? wf.r_pid : wf.h_pid)[s] = pid;
-                (SORT ? wf.r_obj : wf.h_obj)[s] = best.obj;
-                (SORT ? wf.r_order : wf.h_order)[s] = best.order;
-                if constexpr (SORT) {
-                    unsigned int key = sort_cell(sc, P);
-                    wf.r_key[s] = key;
-                    atomicAdd(wf.hist + key, 1u);
-                }
-                double *g = (SORT ? wf.r_geo : wf.h_geo) + s;
-                g[0] = P.x; g[np] = P.y; g[2 * np] = P.z;
-                g[3 * np] = N.x; g[4 * np] = N.y; g[5 * np] = N.z;
-                g[6 * np] = D.x; g[7 * np] = D.y; g[8 * np] = D.z;
+        if (!m) continue;
+        unsigned int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)__popc(m));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (hit) {
+            d3 O, D;
+            int pid;
+            bool valid;
+            path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
+            double t = wf.res_t[i];
+            d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
+            d3 N = hit_normal(sc, r.x, P);
+            size_t s = slot0 + rank_in(m, lane);
+            HitRec rec;
+            rec.P[0] = P.x; rec.P[1] = P.y; rec.P[2] = P.z; rec.obj = r.x; rec.order = r.y;
+            rec.N[0] = N.x; rec.N[1] = N.y; rec.N[2] = N.z; rec.pid = pid; rec.pad0 = 0;
+            rec.D[0] = D.x; rec.D[1] = D.y; rec.D[2] = D.z; rec.pad1 = 0.0;
+            const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + s);
+#pragma unroll
+            for (int k = 0; k < 6; k++) dst[k] = src[k];
+            if constexpr (SORT) {
+                unsigned int key = sort_cell(sc, P);
+                wf.r_key[s] = key;
+                atomicAdd(wf.hist + key, 1u);
             }
         }
     }
-    wf_flush<COUNT>(fp, rays, tl);
 }
 
 // shadow_factor/4 (erl:256-267) of every (light, hit) pair of one bounce, light-major so that a
-// warp holds rays that leave one light towards neighbouring hit locations.
+// warp holds rays that leave one light towards neighbouring hit locations.  A ray is first tried
+// against the sphere that shadowed this lane's previous ray: any object that beats the target's
+// (t, order) settles the question (erl:263), so a neighbour's occluder usually ends the query
+// without a walk.
 template <bool COUNT>
-__global__ void __launch_bounds__(kWfThreads)
+__global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
 wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                 const __grid_constant__ WfBuf wf, int bounce)
 {
-    const unsigned int n_hits = wf.ctr[bounce * kWfCtr + WF_NHITS];
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned int n_hits = ctr[WF_NHITS];
     const unsigned long long total = (unsigned long long)n_hits * (unsigned long long)sc.n_lights;
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_SHADOW);
     const int lane = threadIdx.x & 31;
-    const unsigned int warp = (blockIdx.x * kWfThreads + threadIdx.x) >> 5;
-    const unsigned int n_warps = (gridDim.x * kWfThreads) >> 5;
     const size_t np = (size_t)wf.n_pad;
     Tally<COUNT> tl;
     unsigned int rays = 0;
-    for (unsigned long long base = (unsigned long long)warp * 32; base < total; base += (unsigned long long)n_warps * 32) {
-        unsigned long long j = base + lane;
-        if (j >= total) continue;
-        unsigned int l = (unsigned int)(base / n_hits);
-        unsigned long long h64 = base - (unsigned long long)l * n_hits + lane;
-        while (h64 >= n_hits) { h64 -= n_hits; l++; }
-        size_t h = (size_t)h64;
-        rays++;
-        d3 P = mk(wf.h_geo[h], wf.h_geo[np + h], wf.h_geo[2 * np + h]);
-        int obj = wf.h_obj[h], order = wf.h_order[h];
-        const double *lt = sc.lights + 9 * (size_t)l;
-        d3 O = mk(lt[3], lt[4], lt[5]);
-        d3 D = vnormalize(vsub(P, O));                        // erl:257-260
-        double a = D.x * D.x + D.y * D.y + D.z * D.z;
-        unsigned char lit = 0;
-        double t;
-        // "nearest == Object" (erl:263) <=> Object is hit and nothing beats its (t, order)
-        if (object_exact(sc, obj, O, D, a, t)) {
-            Hit best;
-            best.t = t; best.order = order; best.obj = obj;
-            scan_others<COUNT>(sc, O, D, best, obj, tl);
-            if (best.obj == obj && sc.n_spheres > 0) {
-                SRay f;
-                make_sray(sc, O, D, f);
-                traverse_bvh<true, COUNT>(sc, O, D, f, best, obj, obj, tl);
+    int hint = -1;                                   // sphere that shadowed this lane's previous ray
+    unsigned long long begin, end;
+    while (next_chunk(cursor, total, lane, begin, end)) {
+        for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
+            const unsigned long long j = b0 + lane;
+            if (j >= end) continue;
+            unsigned int l, h;
+            if (total <= 0xffffffffull) {
+                l = (unsigned int)j / n_hits;
+                h = (unsigned int)j - l * n_hits;
+            } else {
+                l = (unsigned int)(j / n_hits);
+                h = (unsigned int)(j - (unsigned long long)l * n_hits);
             }
-            lit = best.obj == obj;
+            rays++;
+            bool lit = false;
+            {
+                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hits + h);
+                d3 P = mk(r0.x, r0.y, r0.z);
+                const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
+                const int order = (int)(__double_as_longlong(r0.w) >> 32);
+                const double *lt = sc.lights + 9 * (size_t)l;
+                d3 O = mk(lt[3], lt[4], lt[5]);
+                d3 D = vnormalize(vsub(P, O));                     // erl:257-260
+                double a = D.x * D.x + D.y * D.y + D.z * D.z;
+                double t;
+                // "nearest == Object" (erl:263) <=> Object is hit and nothing beats its (t, order)
+                if (object_exact(sc, target, O, D, a, t)) {
+                    Hit best;
+                    best.t = t; best.order = order; best.obj = target;
+                    scan_others<COUNT>(sc, O, D, best, target, tl);
+                    lit = best.obj == target;
+                    if (lit && hint >= 0 && obj_code(OBJ_SPHERE, hint) != target) {
+                        double th;
+                        TALLY(exact_sph);
+                        if (sphere_exact(O, D, a, sc.sph_exact[hint], th) && better(th, sc.sph_order[hint], best))
+                            lit = false;
+                    }
+                    if (lit && sc.n_spheres > 0) {
+                        SRay f;
+                        double a2, inv;
+                        make_sray(sc, O, D, f, a2, inv);
+                        ray.put(O, D, a2, inv);
+                        Trav<true> tr;
+                        trav_start(tr, f, inv, best);
+                        while (!trav_step<true, COUNT>(tr, sc, ray, f, best, target, target, tl)) { }
+                        lit = best.obj == target;
+                        if (!lit && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
+                    }
+                }
+            }
+            wf.lit[(size_t)l * np + h] = lit;
         }
-        wf.lit[(size_t)l * np + h] = lit;
     }
-    wf_flush<COUNT>(fp, rays, tl);
+    flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
 // Folds the lights of every hit of one bounce (erl:209-252 in forward form, see pix_consume)
@@ -478,12 +673,16 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
         int pid = 0;
         d3 P = mk(0, 0, 0), N = P, D = P;
         if (valid) {
-            pid = wf.h_pid[h];
-            const double *g = wf.h_geo + h;
-            P = mk(g[0], g[np], g[2 * np]);
-            N = mk(g[3 * np], g[4 * np], g[5 * np]);
-            D = mk(g[6 * np], g[7 * np], g[8 * np]);
-            const double *mat = material_ptr(sc, wf.h_obj[h]);
+            HitRec rec;
+            const uint4 *src = reinterpret_cast<const uint4 *>(wf.hits + h);
+            uint4 *dst = reinterpret_cast<uint4 *>(&rec);
+#pragma unroll
+            for (int k = 0; k < 6; k++) dst[k] = src[k];
+            pid = rec.pid;
+            P = mk(rec.P[0], rec.P[1], rec.P[2]);
+            N = mk(rec.N[0], rec.N[1], rec.N[2]);
+            D = mk(rec.D[0], rec.D[1], rec.D[2]);
+            const double *mat = material_ptr(sc, rec.obj);
             d3 S = mk(0.0, 0.0, 0.0);
             for (int l = 0; l < L; l++) {
                 if (wf.lit[(size_t)l * np + h]) S = vadd(S, light_term(sc.lights + 9 * (size_t)l, mat, P, N, D));
@@ -502,12 +701,11 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
         }
         unsigned int m = __ballot_sync(0xffffffffu, cont);
         if (m) {
-            int leader = __ffs(m) - 1;
             unsigned int slot0 = 0;
-            if (lane == leader) slot0 = atomicAdd(ctr + WF_NNEXT, (unsigned int)__popc(m));
-            slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+            if (lane == 0) slot0 = atomicAdd(ctr + WF_NNEXT, (unsigned int)__popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (cont) {
-                size_t s = slot0 + __popc(m & ((1u << lane) - 1u));
+                size_t s = slot0 + rank_in(m, lane);
                 d3 nd = vbounce(D, N);                            // erl:219-221
                 wf.q_pid[s] = pid;
                 double *q = wf.q_ray + s;
