@@ -488,7 +488,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
 }
 
 template <bool COUNT>
-int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *launches)
+int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorted, uint64_t *launches)
 {
     WfBuf wf{};
     int rc;
@@ -500,7 +500,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *la
     uint64_t n = 0;
     // ERT_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
     static const bool debug_sync = getenv("ERT_DEBUG_SYNC") != nullptr;
-    static const bool no_sort = getenv("ERT_WF_NO_SORT") != nullptr;     // A/B switch for the hit binning
+    const bool no_sort = unsorted || getenv("ERT_WF_NO_SORT") != nullptr;  // A/B switch for the hit binning
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -534,7 +534,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, uint64_t *la
             CU(cudaMemsetAsync(wf.hist, 0, (size_t)kSortCells * sizeof(unsigned int), st));
             wf_emit_hits<false, true><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
             wf_bin_scan_a<<<kSortBlocks, 1024, 0, st>>>(wf);
-            wf_bin_scan_b<<<1, kSortBlocks, 0, st>>>(wf);
+            wf_bin_scan_b<<<1, kSortScanBThreads, 0, st>>>(wf);
             wf_bin_scatter<<<s->wf_grid[3], kWfThreads, 0, st>>>(wf, b);
             n += 3;
         }
@@ -712,8 +712,9 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
     CU(cudaEventRecord(sl.ev0, sl.stream));
     if (fp.local_rows > 0 && accel == ERT_ACCEL_BVH && fp.depth > 0) {
         uint64_t n = 0;
-        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, &n)
-                                              : launch_wavefront<false>(scene, sl, fp, &n);
+        const bool unsorted = (p.flags & ERT_FLAG_WF_UNSORTED) != 0;
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, unsorted, &n);
         if (rc != ERT_OK) return rc;
         sl.stats.gpu_launches = n;
     } else if (fp.local_rows > 0) {

@@ -72,10 +72,16 @@ constexpr int kWfThreads = 256;
 #ifndef ERT_WF_MINBLOCKS
 #define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
 #endif
-constexpr int kSortBits = 7;                                  // per axis
-constexpr int kSortCells = 1 << (3 * kSortBits);              // 2 Mi cells over the sphere bounds
-constexpr int kSortScanBlock = 4096;                          // cells scanned by one block
-constexpr int kSortBlocks = kSortCells / kSortScanBlock;      // 512
+#ifndef ERT_WF_SORT_BITS
+#define ERT_WF_SORT_BITS 8
+#endif
+constexpr int kSortBits = ERT_WF_SORT_BITS;                   // per axis
+constexpr int kSortCells = 1 << (3 * kSortBits);              // bins of the counting sort (16 Mi)
+constexpr int kSortScanBlock = 4096;                          // bins scanned by one block
+constexpr int kSortBlocks = kSortCells / kSortScanBlock;
+constexpr int kSortScanBThreads = kSortBlocks < 1024 ? kSortBlocks : 1024;
+constexpr int kSortScanBItems = kSortBlocks / kSortScanBThreads;
+static_assert(kSortBlocks % 32 == 0 && kSortBlocks <= 8192, "scan phase B is one block");
 // ------------------------------------------------------------------ slim ray for the traversal
 // Same bounds as FRay (DESIGN.md "Filter bounds"); the slab constants are written so that the
 // near/far choice needs no select: with m the absolute margin,
@@ -353,6 +359,8 @@ __device__ __forceinline__ unsigned int part1by2(unsigned int x)
     x = (x | (x << 2)) & 0x9249249u;
     return x;
 }
+// (Measured and dropped: a grid narrowed to mean +- k sigma of the previous bounce's hits; the octant of
+// the reflected direction as the leading key bits.  7 -> 8 bits per axis was worth 9 % on C4.)
 __device__ __forceinline__ unsigned int sort_cell(const DevScene &sc, d3 P)
 {
     const float top = (float)((1 << kSortBits) - 1);
@@ -395,11 +403,15 @@ __global__ void __launch_bounds__(1024) wf_bin_scan_a(const __grid_constant__ Wf
     *reinterpret_cast<uint4 *>(h) = o;
 }
 // phase B: exclusive scan of the kSortBlocks block totals (one block)
-__global__ void __launch_bounds__(kSortBlocks) wf_bin_scan_b(const __grid_constant__ WfBuf wf)
+__global__ void __launch_bounds__(kSortScanBThreads) wf_bin_scan_b(const __grid_constant__ WfBuf wf)
 {
     __shared__ unsigned int warp_sums[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int t = wf.sums[threadIdx.x], incl = t;
+    unsigned int v[kSortScanBItems];
+    unsigned int t = 0;
+#pragma unroll
+    for (int k = 0; k < kSortScanBItems; k++) { v[k] = wf.sums[threadIdx.x * kSortScanBItems + k]; t += v[k]; }
+    unsigned int incl = t;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         unsigned int o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(kSortBlocks) wf_bin_scan_b(const __grid_consta
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        unsigned int w = lane < kSortBlocks / 32 ? warp_sums[lane] : 0u, wi = w;
+        unsigned int w = lane < kSortScanBThreads / 32 ? warp_sums[lane] : 0u, wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned int o = __shfl_up_sync(0xffffffffu, wi, d);
@@ -417,7 +429,9 @@ __global__ void __launch_bounds__(kSortBlocks) wf_bin_scan_b(const __grid_consta
         warp_sums[lane] = wi - w;
     }
     __syncthreads();
-    wf.sums[threadIdx.x] = warp_sums[warp] + incl - t;
+    unsigned int run = warp_sums[warp] + incl - t;
+#pragma unroll
+    for (int k = 0; k < kSortScanBItems; k++) { wf.sums[threadIdx.x * kSortScanBItems + k] = run; run += v[k]; }
 }
 // scatter: every raw hit record moves to its cell's range of the sorted hit queue
 __global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_constant__ WfBuf wf, int bounce)

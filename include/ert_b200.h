@@ -121,6 +121,8 @@ typedef struct ert_scene_desc {
 #define ERT_ACCEL_BVH_MEGAKERNEL 4  /* same BVH, one launch, per-pixel state machine (kept as a cross-check) */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
+#define ERT_FLAG_WF_UNSORTED  2u  /* ERT_ACCEL_BVH: skip the binning of hits by location (A/B switch; the
+                                   * frame is identical, only the schedule of the queues changes) */
 
 typedef struct ert_render_params {
     int32_t width, height;      /* pixels, both > 0 (guards at erl:89) */

@@ -329,3 +329,68 @@ def test_c4_full_4k_bvh_equals_linear_scan_and_oracle_samples(gpu):
     ref, _, _ = oracle_frame(flat, w, h, depth, pixels=(xs, ys))
     assert_double_parity(full[ys, xs], ref)
     dev.close()
+
+
+# ---- wavefront form of the BVH path (ERT_ACCEL_BVH) -----------------------------------------
+def test_wavefront_binned_queues_render_the_same_frame(gpu):
+    """Binning the hit queue by location only reschedules rays: frame and ray count are unchanged."""
+    flat = sc.synthetic_scene("c3")
+    dev = flat.upload(0)
+    w, h, depth = 640, 360, 5
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_WF_UNSORTED)
+    c, sc_ = dev.render(w, h, depth, fmt="f64", accel="bvh_mega")
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert sa["rays"] == sb["rays"] == sc_["rays"]
+    assert sa["gpu_launches"] > sb["gpu_launches"] > sc_["gpu_launches"] == 1
+    # instrumented run: same frame, counters filled
+    d, sd = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
+    assert np.array_equal(a, d) and sd["box_tests"] > 0 and sd["sphere_filter_tests"] > 0
+    dev.close()
+
+
+def test_wavefront_deep_recursion_stops_when_the_queue_runs_dry(gpu):
+    """Depths past 8 poll the path-queue length between bounces (ert_api.cu launch_wavefront)."""
+    scene = [CAM, L1, L2] + [('sphere', 1.0, ('vector', 2.5 * i - 5, 0.3 * i, 8 + i),
+                              mat((0.2 + 0.1 * i, 0.5, 0.9 - 0.1 * i), 4, 0.5, 0.6)) for i in range(5)]
+    scene.append(('plane', ('vector', 0, -1, 0), 3, mat((1, 1, 1), 1, 0, 0.3)))
+    check_scene(scene, 48, 36, 14, accels=("exact", "bvh", "bvh_mega"))
+
+
+@pytest.mark.parametrize("n_lights", [1, 5])
+def test_wavefront_light_counts(gpu, n_lights):
+    lights = [('point_light', ('colour', 0.3 + 0.1 * k, 0.5, 0.2 * k), ('vector', 6 * k - 10, -8, -3 + 2 * k),
+               ('colour', 1, 1, 1)) for k in range(n_lights)]
+    flat = sc.synthetic_scene("c3", n_spheres=3000)
+    scene_lights = np.zeros(n_lights, dtype=_lib.LIGHT_DT)
+    for k, l in enumerate(lights):
+        scene_lights[k]['diffuse_colour'] = l[1][1:]
+        scene_lights[k]['location'] = l[2][1:]
+        scene_lights[k]['specular_colour'] = l[3][1:]
+        scene_lights[k]['order'] = k
+    flat.spheres['order'] = np.arange(n_lights, n_lights + len(flat.spheres), dtype=np.int32)
+    flat.planes['order'] = n_lights + len(flat.spheres)
+    flat.lights = scene_lights
+    dev = flat.upload(0)
+    w, h, depth = 96, 54, 4
+    ref, ref_rays, _ = oracle_frame(flat, w, h, depth)
+    for accel in ("bvh", "bvh_mega"):
+        frame, st = dev.render(w, h, depth, fmt="f64", accel=accel)
+        assert_double_parity(frame, ref)
+        assert np.array_equal(quantise(frame), quantise(ref))
+        assert st["rays"] == ref_rays
+    dev.close()
+
+
+def test_wavefront_row_band_parts_assemble_the_frame(gpu):
+    flat = sc.synthetic_scene("c3", n_spheres=5000)
+    dev = flat.upload(0)
+    w, h, depth = 250, 131, 4                      # ragged: width not a multiple of 8, partial last band
+    full, st = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    out = np.zeros_like(full)
+    rays = 0
+    for part in range(3):
+        _, sp = dev.render(w, h, depth, fmt="f64", accel="bvh", band_rows=8, n_parts=3, part=part, out=out)
+        rays += sp["rays"]
+    assert np.array_equal(out, full) and rays == st["rays"]
+    dev.close()
