@@ -459,6 +459,10 @@ __device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc
 #define ERT_WF_CHUNK 128
 #endif
 constexpr unsigned int kWfChunk = ERT_WF_CHUNK;
+#ifndef ERT_WF_OCC_CACHE
+#define ERT_WF_OCC_CACHE 8
+#endif
+constexpr int kOccCache = ERT_WF_OCC_CACHE;      // recent occluders a warp remembers (wf_trace_shadow)
 static_assert(kWfChunk % 32 == 0, "chunks are whole batches");
 
 __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned long long total, int lane,
@@ -611,11 +615,23 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
     Tally<COUNT> tl;
     unsigned int rays = 0;
     int hint = -1;                                   // sphere that shadowed this lane's previous ray
+    // the warp's recent occluders: filter sphere + index, a ring the whole warp reads by broadcast
+    __shared__ float4 occ_f_all[kWfThreads / 32][kOccCache];
+    __shared__ int occ_i_all[kWfThreads / 32][kOccCache];
+    float4 *occ_f = occ_f_all[threadIdx.x >> 5];
+    int *occ_i = occ_i_all[threadIdx.x >> 5];
+    for (int k = lane; k < kOccCache; k += 32) {
+        occ_f[k] = make_float4(0.f, 0.f, 0.f, -3.0e38f);       // never passes the filter
+        occ_i[k] = -1;
+    }
+    int occ_head = 0;
+    __syncwarp();
     unsigned long long begin, end;
     while (next_chunk(cursor, total, lane, begin, end)) {
         for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
             const unsigned long long j = b0 + lane;
-            if (j >= end) continue;
+            int found = -1;                          // sphere a walk of this batch found in the way
+            if (j < end) {
             unsigned int l, h;
             if (total <= 0xffffffffull) {
                 l = (unsigned int)j / n_hits;
@@ -652,16 +668,55 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                         SRay f;
                         double a2, inv;
                         make_sray(sc, O, D, f, a2, inv);
-                        ray.put(O, D, a2, inv);
-                        Trav<true> tr;
-                        trav_start(tr, f, inv, best);
-                        while (!trav_step<true, COUNT>(tr, sc, ray, f, best, target, target, tl)) { }
-                        lit = best.obj == target;
-                        if (!lit && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
+                        // the warp's recent occluders, FP32 filter first
+                        const float cull0 = cullk_from(f, inv, best);
+                        for (int k = 0; k < kOccCache && lit; k++) {
+                            const float4 fs = occ_f[k];
+                            float fb, fv;
+                            TALLY(filter);
+                            if (filter_stage1(f, fs, fb, fv) && filter_stage2(f, fs, fb, fv, cull0)) {
+                                const int sph = occ_i[k];
+                                if (obj_code(OBJ_SPHERE, sph) != target) {
+                                    double th;
+                                    TALLY(exact_sph);
+                                    if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) {
+                                        lit = false;
+                                        hint = sph;
+                                    }
+                                }
+                            }
+                        }
+                        if (lit) {
+                            ray.put(O, D, a2, inv);
+                            Trav<true> tr;
+                            trav_start(tr, f, inv, best);
+                            while (!trav_step<true, COUNT>(tr, sc, ray, f, best, target, target, tl)) { }
+                            lit = best.obj == target;
+                            if (!lit && obj_type(best.obj) == OBJ_SPHERE) { hint = obj_index(best.obj); found = hint; }
+                        }
                     }
                 }
             }
             wf.lit[(size_t)l * np + h] = lit;
+            }
+            // new occluders enter the warp's ring (one lane per distinct sphere)
+            const unsigned int fm = __ballot_sync(0xffffffffu, found >= 0);
+            if (fm) {
+                bool ins = false;
+                if (found >= 0) {
+                    const unsigned int same = __match_any_sync(fm, found);
+                    ins = (__ffs(same) - 1) == lane;
+                }
+                const unsigned int im = __ballot_sync(0xffffffffu, ins);
+                __syncwarp();
+                if (ins) {
+                    const int slot = (occ_head + rank_in(im, lane)) % kOccCache;
+                    occ_f[slot] = __ldg(sc.sph_filter + found);
+                    occ_i[slot] = found;
+                }
+                occ_head = (occ_head + __popc(im)) % kOccCache;
+                __syncwarp();
+            }
         }
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
