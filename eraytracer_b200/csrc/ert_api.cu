@@ -18,6 +18,10 @@
 #include "ert_device.cuh"
 #include "ert_wavefront.cuh"
 
+#ifndef ERT_WF_REFILL_FROM
+#define ERT_WF_REFILL_FROM 2        /* first bounce whose path rays use the refilling kernel */
+#endif
+
 using namespace ert;
 
 namespace {
@@ -522,7 +526,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorte
         }
         const bool sort = b >= 1 && !no_sort;
         if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_path_refill<COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         n++;
         WF_CHECK("wf_trace_path");
         if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)

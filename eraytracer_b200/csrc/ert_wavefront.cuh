@@ -544,6 +544,94 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
+// Path rays of bounces >= 1 have nothing to do with their queue neighbours (they leave curved
+// surfaces in all directions), walks differ in length several-fold, and a batch of 32 waits for
+// its longest one.  This form keeps the warp resident and hands new rays to lanes that have
+// finished once fewer than kRefillBelow lanes are still walking.  (Set-up of a path ray is a
+// queue read and a plane test, cheap enough to run on a few lanes at a time; for shadow rays,
+// whose set-up is heavy FP64, the same scheme lost.)
+#ifndef ERT_WF_REFILL
+#define ERT_WF_REFILL 20
+#endif
+constexpr int kRefillBelow = ERT_WF_REFILL;
+#ifndef ERT_WF_REFILL_MINBLOCKS
+#define ERT_WF_REFILL_MINBLOCKS 3
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(kWfThreads, ERT_WF_REFILL_MINBLOCKS)
+wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
+                     const __grid_constant__ WfBuf wf, int bounce)
+{
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned long long n = (unsigned long long)wf.ctr[(bounce - 1) * kWfCtr + WF_NNEXT];
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_PATH);
+    const int lane = threadIdx.x & 31;
+    Tally<COUNT> tl;
+    unsigned int rays = 0;
+    bool have = false;
+    unsigned long long pos = 0, end = 0;             // the warp's current chunk
+    bool drained = false;                            // no chunk left in the queue
+    unsigned int idx = 0;
+    SRay f;
+    Hit best;
+    best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+    Trav<false> tr;
+    tr.node = kTravDone; tr.sp = 0; tr.cullk = 0.f;
+    for (;;) {
+        const unsigned int idle = __ballot_sync(0xffffffffu, !have);
+        if (32 - __popc(idle) < kRefillBelow && !drained) {
+            if (pos >= end) {
+                if (!next_chunk(cursor, n, lane, pos, end)) { drained = true; pos = end = 0; }
+            }
+            if (pos < end) {
+                const unsigned long long i64 = pos + (unsigned long long)rank_in(idle, lane);
+                const unsigned long long adv = pos + (unsigned long long)__popc(idle);
+                pos = adv < end ? adv : end;
+                if (!have && i64 < end) {
+                    const unsigned int i = (unsigned int)i64;
+                    bool valid;
+                    int pid;
+                    d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
+                    path_ray_of_index(fp, wf, false, i, O, D, pid, valid);
+                    idx = i;
+                    rays++;
+                    best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+                    scan_others<COUNT>(sc, O, D, best, -1, tl);
+                    if (sc.n_spheres > 0) {
+                        double a, inv;
+                        make_sray(sc, O, D, f, a, inv);
+                        ray.put(O, D, a, inv);
+                        trav_start(tr, f, inv, best);
+                        have = true;
+                    } else {
+                        wf.res_hit[i] = make_int2(best.obj, best.order);
+                        wf.res_t[i] = best.t;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (drained) break;
+            continue;
+        }
+        for (;;) {
+            if (have) {
+                if (trav_step<false, COUNT>(tr, sc, ray, f, best, -1, -1, tl)) {
+                    wf.res_hit[idx] = make_int2(best.obj, best.order);
+                    wf.res_t[idx] = best.t;
+                    have = false;
+                }
+            }
+            const int act = __popc(__ballot_sync(0xffffffffu, have));
+            if (act == 0 || (!drained && act < kRefillBelow)) break;
+        }
+    }
+    flush_counters<COUNT>(fp, (int)rays, tl);
+}
+
 // Turns the nearest-hit results of one bounce into the hit queue: hit location and normal
 // (erl:384-390, 443-451, 471-476), compaction, and (SORT) the cell histogram for the binning.
 template <bool FIRST, bool SORT>
