@@ -17,6 +17,7 @@ FMT_RGB8, FMT_F32, FMT_F64 = 0, 1, 2
 ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL = 0, 1, 2, 3, 4
 FLAG_COUNT_TESTS = 1
 FLAG_WF_UNSORTED = 2
+FLAG_NO_LIGHT_GRID = 4
 MAX_SLOTS = 4
 
 FORMATS = {"rgb8": FMT_RGB8, "f32": FMT_F32, "f64": FMT_F64}

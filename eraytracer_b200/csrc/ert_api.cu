@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "bvh_build.h"
+#include "light_grid.h"
 #include "ert_device.cuh"
 #include "ert_wavefront.cuh"
 
@@ -60,6 +61,7 @@ struct HostScene {
     std::vector<float> sph_filter;     // [n][4]
     std::vector<float> leaf_filter;    // [n][4]
     Bvh bvh;
+    std::vector<LightGrid> lgrids;     // direction grids of the first lights (shadow queries)
     float r_max = 0, pad_c_max = 0, eta_c_max = 0, abs_max = 0;
     float grid_lo[3] = {0, 0, 0}, grid_scale[3] = {0, 0, 0};
     int n_lights = 0, n_planes = 0, n_tris = 0, n_spheres = 0;
@@ -259,6 +261,18 @@ int flatten(const ert_scene_desc *d, HostScene &h)
             if (!std::isfinite(h.grid_scale[a]) || !std::isfinite(h.grid_lo[a])) { h.grid_lo[a] = 0; h.grid_scale[a] = 0; }
         }
     }
+    {
+        // direction grids for shadow rays: worth their memory once a walk through the BVH costs more
+        // than a handful of candidate tests; ERT_LIGHT_GRID_RES=0 turns them off
+        int res = kLightGridRes;
+        if (const char *e = getenv("ERT_LIGHT_GRID_RES")) res = atoi(e);
+        res = std::min(std::max(res, 0), 1024);
+        int n_grids = (res > 0 && h.n_spheres >= kLightGridMinSpheres) ? std::min(h.n_lights, kMaxLightGrids) : 0;
+        h.lgrids.resize((size_t)n_grids);
+        for (int g = 0; g < n_grids; g++)
+            build_light_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, &h.lights[(size_t)g * 9 + 3],
+                             res, h.lgrids[(size_t)g]);
+    }
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
@@ -306,6 +320,28 @@ int upload_scene(ert_scene *s)
     UP(h.bvh.leaf_prim, leaf_sph, int);
     UP(h.bvh.nodes, nodes, BvhNode);
 #undef UP
+    {
+        std::vector<LightGridDev> lg(h.lgrids.size());
+        for (size_t g = 0; g < h.lgrids.size(); g++) {
+            const LightGrid &G = h.lgrids[g];
+            std::vector<LightGridCand> cand(G.entries.size());
+            for (size_t e = 0; e < cand.size(); e++) {
+                LightGridCand &c = cand[e];
+                c.cx = G.fs[4 * e]; c.cy = G.fs[4 * e + 1]; c.cz = G.fs[4 * e + 2]; c.R = G.fs[4 * e + 3];
+                c.sphere = G.entries[e].sphere; c.dmin = G.entries[e].dmin; c.pad[0] = c.pad[1] = 0;
+            }
+            const unsigned int *off; const LightGridCand *cd; const int *al;
+            if ((rc = upload<unsigned int>(s, G.cell_off, &off)) != ERT_OK) return rc;
+            if ((rc = upload<LightGridCand>(s, cand, &cd)) != ERT_OK) return rc;
+            if ((rc = upload<int>(s, G.always, &al)) != ERT_OK) return rc;
+            lg[g].cell_off = off; lg[g].cand = cd; lg[g].always = al;
+            lg[g].n_always = (int)G.always.size(); lg[g].res = G.res;
+        }
+        const LightGridDev *lgd;
+        if ((rc = upload<LightGridDev>(s, lg, &lgd)) != ERT_OK) return rc;
+        d.lgrids = lgd;
+        d.lg_count = (int)lg.size();
+    }
     d.n_nodes = (int)h.bvh.nodes.size();
     for (int a = 0; a < 3; a++) { d.grid_lo[a] = h.grid_lo[a]; d.grid_scale[a] = h.grid_scale[a]; }
     d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
@@ -331,7 +367,7 @@ int upload_scene(ert_scene *s)
         s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false>, kWfThreads, 0));
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false, true>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
         s->wf_grid[3] = prop.multiProcessorCount * std::max(nb, 1);
@@ -492,7 +528,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
 }
 
 template <bool COUNT>
-int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorted, uint64_t *launches)
+int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorted, bool no_grid, uint64_t *launches)
 {
     WfBuf wf{};
     int rc;
@@ -545,7 +581,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorte
         }
         n++;
         WF_CHECK("wf_emit_hits / wf_bin_*");
-        wf_trace_shadow<COUNT><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
+        if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
         WF_CHECK("wf_trace_shadow");
         wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
         n += 2;
@@ -718,8 +755,9 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
     if (fp.local_rows > 0 && accel == ERT_ACCEL_BVH && fp.depth > 0) {
         uint64_t n = 0;
         const bool unsorted = (p.flags & ERT_FLAG_WF_UNSORTED) != 0;
-        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, &n)
-                                              : launch_wavefront<false>(scene, sl, fp, unsorted, &n);
+        const bool no_grid = (p.flags & ERT_FLAG_NO_LIGHT_GRID) != 0;
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, &n);
         if (rc != ERT_OK) return rc;
         sl.stats.gpu_launches = n;
     } else if (fp.local_rows > 0) {

@@ -56,6 +56,24 @@ struct DevScene {
     float abs_max;               // largest |coordinate| of any sphere box
     // uniform grid over the sphere bounds, used only to order the wavefront queues
     float grid_lo[3], grid_scale[3];
+    // direction grids of the first lg_count lights (light_grid.h): shadow-ray candidates by direction
+    const struct LightGridDev *lgrids;
+    int lg_count;
+};
+
+// One entry of a light's direction grid: 32 bytes, one 256-bit load.
+struct alignas(32) LightGridCand {
+    float cx, cy, cz, R;         // filter sphere
+    int sphere;                  // sphere index
+    float dmin;                  // lower bound of the distance light -> sphere
+    int pad[2];
+};
+struct LightGridDev {
+    const unsigned int *cell_off;    // [6*res*res + 1]
+    const LightGridCand *cand;       // nearest first inside a cell
+    const int *always;               // spheres that contain the light: candidates of every ray
+    int n_always;
+    int res;
 };
 
 struct FrameParams {

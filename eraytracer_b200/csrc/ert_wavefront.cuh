@@ -447,6 +447,58 @@ __global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------ shadow queries by direction
+// Cell of a direction in a light's cube map; restates light_grid_cell() of light_grid.cpp.
+__device__ __forceinline__ unsigned int light_grid_cell_dev(d3 D, int res)
+{
+    double ax = fabs(D.x), ay = fabs(D.y), az = fabs(D.z);
+    int m = 0;
+    double am = ax, dm = D.x, du = D.y, dv = D.z;
+    if (ay > am) { m = 1; am = ay; dm = D.y; du = D.z; dv = D.x; }
+    if (az > am) { m = 2; am = az; dm = D.z; du = D.x; dv = D.y; }
+    int face = 2 * m + (dm < 0.0 ? 1 : 0);
+    double u = du / am, v = dv / am;
+    int iu = (int)floor((u + 1.0) * 0.5 * (double)res), iv = (int)floor((v + 1.0) * 0.5 * (double)res);
+    iu = min(max(iu, 0), res - 1);
+    iv = min(max(iv, 0), res - 1);
+    return (unsigned int)((face * res + iv) * res + iu);
+}
+
+// Is any sphere in the way of the shadow ray (O = the light, D) before its target?  `best` holds
+// the target as incumbent.  Candidates come from the light's direction grid, nearest first; each
+// goes through the FP32 filter and then the literal FP64 test, exactly like a BVH leaf sphere.
+template <bool COUNT>
+__device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const LightGridDev &lg, const SRay &f, d3 O,
+                                                    d3 D, double a, double inv_sqrt_a, const Hit &best, int target,
+                                                    Tally<COUNT> &tl)
+{
+    const float cull0 = cullk_from(f, inv_sqrt_a, best);
+    const unsigned int cell = light_grid_cell_dev(D, lg.res);
+    const unsigned int e0 = __ldg(lg.cell_off + cell), e1 = __ldg(lg.cell_off + cell + 1);
+    for (unsigned int e = e0; e < e1; e++) {
+        float c[8];
+        ldg256(lg.cand + e, c);
+        if (c[5] > cull0) break;                         // this and all later candidates lie beyond the target
+        const float4 fs = make_float4(c[0], c[1], c[2], c[3]);
+        float fb, fv;
+        TALLY(filter);
+        if (!filter_stage1(f, fs, fb, fv) || !filter_stage2(f, fs, fb, fv, cull0)) continue;
+        const int sph = __float_as_int(c[4]);
+        if (obj_code(OBJ_SPHERE, sph) == target) continue;
+        double th;
+        TALLY(exact_sph);
+        if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+    }
+    for (int k = 0; k < lg.n_always; k++) {
+        const int sph = lg.always[k];
+        if (obj_code(OBJ_SPHERE, sph) == target) continue;
+        double th;
+        TALLY(exact_sph);
+        if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------ kernels
 // lanes below `lane` in mask m
 __device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc(m & ((1u << lane) - 1u)); }
@@ -686,7 +738,7 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
 // against the sphere that shadowed this lane's previous ray: any object that beats the target's
 // (t, order) settles the question (erl:263), so a neighbour's occluder usually ends the query
 // without a walk.
-template <bool COUNT>
+template <bool COUNT, bool USE_GRID>
 __global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
 wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                 const __grid_constant__ WfBuf wf, int bounce)
@@ -752,7 +804,13 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                         if (sphere_exact(O, D, a, sc.sph_exact[hint], th) && better(th, sc.sph_order[hint], best))
                             lit = false;
                     }
-                    if (lit && sc.n_spheres > 0) {
+                    if (lit && sc.n_spheres > 0 && USE_GRID && l < (unsigned int)sc.lg_count) {
+                        // this light has a direction grid: a few candidates, no walk
+                        SRay f;
+                        double a2, inv;
+                        make_sray(sc, O, D, f, a2, inv);
+                        lit = !light_grid_occluded<COUNT>(sc, sc.lgrids[l], f, O, D, a, inv, best, target, tl);
+                    } else if (lit && sc.n_spheres > 0) {
                         SRay f;
                         double a2, inv;
                         make_sray(sc, O, D, f, a2, inv);

@@ -121,6 +121,8 @@ typedef struct ert_scene_desc {
 #define ERT_ACCEL_BVH_MEGAKERNEL 4  /* same BVH, one launch, per-pixel state machine (kept as a cross-check) */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
+#define ERT_FLAG_NO_LIGHT_GRID 4u /* ERT_ACCEL_BVH: shadow rays walk the BVH even for lights that have a
+                                   * direction grid (A/B switch; same frame) */
 #define ERT_FLAG_WF_UNSORTED  2u  /* ERT_ACCEL_BVH: skip the binning of hits by location (A/B switch; the
                                    * frame is identical, only the schedule of the queues changes) */
 
