@@ -338,9 +338,10 @@ __device__ __forceinline__ void path_ray_of_index(const FrameParams &fp, const W
     } else {
         const size_t np = (size_t)wf.n_pad;
         valid = true;
-        pid = wf.q_pid[i];
-        O = mk(wf.q_ray[i], wf.q_ray[np + i], wf.q_ray[2 * np + i]);
-        D = mk(wf.q_ray[3 * np + i], wf.q_ray[4 * np + i], wf.q_ray[5 * np + i]);
+        // queue traffic is read once: streaming loads keep it from evicting the BVH
+        pid = __ldcs(wf.q_pid + i);
+        O = mk(__ldcs(wf.q_ray + i), __ldcs(wf.q_ray + np + i), __ldcs(wf.q_ray + 2 * np + i));
+        D = mk(__ldcs(wf.q_ray + 3 * np + i), __ldcs(wf.q_ray + 4 * np + i), __ldcs(wf.q_ray + 5 * np + i));
     }
 }
 
@@ -589,8 +590,8 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     }
                 }
             }
-            wf.res_hit[i] = make_int2(valid ? best.obj : -1, best.order);
-            wf.res_t[i] = best.t;
+            __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
+            __stcs(wf.res_t + i, best.t);
         }
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
@@ -607,7 +608,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
 #endif
 constexpr int kRefillBelow = ERT_WF_REFILL;
 #ifndef ERT_WF_REFILL_MINBLOCKS
-#define ERT_WF_REFILL_MINBLOCKS 3
+#define ERT_WF_REFILL_MINBLOCKS 4
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(kWfThreads, ERT_WF_REFILL_MINBLOCKS)
@@ -672,8 +673,8 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
         for (;;) {
             if (have) {
                 if (trav_step<false, COUNT>(tr, sc, ray, f, best, -1, -1, tl)) {
-                    wf.res_hit[idx] = make_int2(best.obj, best.order);
-                    wf.res_t[idx] = best.t;
+                    __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
+                    __stcs(wf.res_t + idx, best.t);
                     have = false;
                 }
             }

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 140 -c 36 --csv --log-file gpurun_out/wf_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 24 --csv --log-file gpurun_out/wf_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:wf_trace -s 10 -c 6 -o gpurun_out/prof_wf $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wf_trace -s 10 -c 5 -o gpurun_out/prof_wf $CMD > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -8
