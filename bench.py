@@ -104,6 +104,20 @@ class ClockSampler:
             os.unlink(self.tmp.name)
         except OSError:
             pass
+        if not clocks:
+            # the timed region was shorter than the sampling period: one synchronous sample right after it
+            try:
+                txt = subprocess.run(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=20).stdout
+                parts = [p.strip() for p in txt.strip().split(",")]
+                if len(parts) >= 8:
+                    clocks.append(float(parts[1])); maxes.append(float(parts[2])); power.append(float(parts[3]))
+                    for nm, val in zip(names, parts[4:8]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+                    out["note"] = "timed region shorter than the 100 ms sampling period; sampled once right after it"
+            except Exception:
+                pass
         if clocks:
             out["sm_mhz"] = statistics.median(clocks)
             out["sm_max_mhz"] = max(maxes)
@@ -266,14 +280,18 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     kernel_ms, rays = 0.0, 0
     launches = 0
+    split = {"path_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "path_launches": 0, "shadow_launches": 0}
     for i in range(args.steps):
         _lib.l2_flush(local_rank)
-        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), **common)
+        # per-launch CUDA events (two per kernel on the launching stream) split the frame by kernel class
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), flags=_lib.FLAG_TIME_KERNELS, **common)
         dev.wait(0)
         st = dev.stats(0)
         kernel_ms += st["kernel_ms"]
         rays += st["rays"]
         launches += st["gpu_launches"]
+        for k in split:
+            split[k] += st[k]
     barrier()
     kernel_ms_max = reduce(kernel_ms, "max")
     rays_all = reduce(rays, "sum")
@@ -311,10 +329,17 @@ def gpu_arm(args, rank, world, local_rank):
         value = rays_all / steps / (ms_per_step * 1e-3) / 1e6
         e2e_ms = 1e3 * e2e_wall_max / steps
         e2e_value = rays_all / steps / (e2e_ms * 1e-3) / 1e6
-        # roofline of the dominant kernel (rank 0's launch): FP32 filter work / kernel time
-        lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10
+        # roofline (rank 0's launches).  Wavefront frames: the dominant kernel class is the BVH walk of
+        # the path rays (wf_trace_path / wf_trace_path_refill); other accels are one kernel per frame.
         k_s = (kernel_ms / steps) * 1e-3
-        achieved = lane_instr / k_s
+        frame_lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10
+        wavefront = counted["accel_used"] == "bvh" and split["path_launches"] > 0
+        if wavefront:
+            lane_instr = counted["path_box_tests"] * 6 + counted["path_filter_tests"] * 10
+            dom_s = (split["path_ms"] / steps) * 1e-3
+        else:
+            lane_instr, dom_s = frame_lane_instr, k_s
+        achieved = lane_instr / dom_s
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -348,13 +373,23 @@ def gpu_arm(args, rank, world, local_rank):
             "roofline": {
                 "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"bvh": "wf_trace_shadow + wf_trace_path (BVH traversal kernels of the wavefront)",
+                "kernel": {"bvh": "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
                            "bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
                            "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?"),
-                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test, "
-                              "counts from an instrumented run of the same frame on rank 0",
-                "box_tests": int(counted["box_tests"]), "sphere_filter_tests": int(counted["sphere_filter_tests"]),
+                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test of the "
+                              "named kernels (counts from an instrumented run of the same frame on rank 0), divided "
+                              "by their CUDA-event time inside the timed steps",
+                "launches_per_step": (split["path_launches"] / steps) if wavefront else 1,
+                "avg_launch_ms": (split["path_ms"] / max(split["path_launches"], 1)) if wavefront else kernel_ms / steps,
+                "share_of_step": (split["path_ms"] / kernel_ms) if wavefront else 1.0,
+                "box_tests": int(counted["path_box_tests"] if wavefront else counted["box_tests"]),
+                "sphere_filter_tests": int(counted["path_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
                 "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
+                "frame": {"lane_instr": int(frame_lane_instr), "frac": frame_lane_instr / k_s / peak,
+                          "box_tests": int(counted["box_tests"]),
+                          "sphere_filter_tests": int(counted["sphere_filter_tests"]),
+                          "ms": {"path": split["path_ms"] / steps, "shadow": split["shadow_ms"] / steps,
+                                 "other": split["other_ms"] / steps, "all": kernel_ms / steps}},
                 "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
                 "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
             },
@@ -383,7 +418,7 @@ def gpu_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))

@@ -18,6 +18,7 @@ ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL = 0, 1, 2
 FLAG_COUNT_TESTS = 1
 FLAG_WF_UNSORTED = 2
 FLAG_NO_LIGHT_GRID = 4
+FLAG_TIME_KERNELS = 8
 MAX_SLOTS = 4
 
 FORMATS = {"rgb8": FMT_RGB8, "f32": FMT_F32, "f64": FMT_F64}
@@ -65,7 +66,11 @@ class Stats(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_uint64), ("sphere_filter_tests", ctypes.c_uint64),
                 ("box_tests", ctypes.c_uint64), ("exact_sphere_tests", ctypes.c_uint64),
                 ("exact_other_tests", ctypes.c_uint64), ("accel_used", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("reserved", ctypes.c_int32),
+                ("path_box_tests", ctypes.c_uint64), ("path_filter_tests", ctypes.c_uint64),
+                ("shadow_box_tests", ctypes.c_uint64), ("shadow_filter_tests", ctypes.c_uint64),
+                ("path_ms", ctypes.c_double), ("shadow_ms", ctypes.c_double), ("other_ms", ctypes.c_double),
+                ("path_launches", ctypes.c_uint64), ("shadow_launches", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

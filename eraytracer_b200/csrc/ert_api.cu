@@ -78,6 +78,8 @@ struct Slot {
     unsigned int *wf_ctr = nullptr;
     int wf_ctr_depth = 0;
     unsigned int *wf_ctr_host = nullptr;           // pinned, for the early-out check of deep recursions
+    std::vector<cudaEvent_t> ticks;                // ERT_FLAG_TIME_KERNELS: one event before/after every launch
+    std::vector<int> tick_class;                   // class of the launch between ticks[i] and ticks[i+1]
     unsigned long long *counters_dev = nullptr;
     unsigned long long *counters_host = nullptr;   // pinned
     ert_render_params params{};
@@ -351,8 +353,8 @@ int upload_scene(ert_scene *s)
         CU(cudaEventCreate(&sl.ev0));
         CU(cudaEventCreate(&sl.ev1));
         CU(cudaEventCreate(&sl.ev2));
-        CU(cudaMalloc(&sl.counters_dev, CNT_N * sizeof(unsigned long long)));
-        CU(cudaMallocHost(&sl.counters_host, CNT_N * sizeof(unsigned long long)));
+        CU(cudaMalloc(&sl.counters_dev, kCounterSets * CNT_N * sizeof(unsigned long long)));
+        CU(cudaMallocHost(&sl.counters_host, kCounterSets * CNT_N * sizeof(unsigned long long)));
     }
     // opt in to the 64 KB double buffer of the tiled kernel
     CU(cudaFuncSetAttribute(render_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -386,6 +388,7 @@ void destroy(ert_scene *s)
         if (sl.wf_mem) cudaFree(sl.wf_mem);
         if (sl.wf_ctr) cudaFree(sl.wf_ctr);
         if (sl.wf_ctr_host) cudaFreeHost(sl.wf_ctr_host);
+        for (cudaEvent_t e : sl.ticks) cudaEventDestroy(e);
         if (sl.counters_dev) cudaFree(sl.counters_dev);
         if (sl.counters_host) cudaFreeHost(sl.counters_host);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
@@ -528,12 +531,31 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
 }
 
 template <bool COUNT>
-int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorted, bool no_grid, uint64_t *launches)
+int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unsorted, bool no_grid, bool timed,
+                     uint64_t *launches)
 {
     WfBuf wf{};
     int rc;
+    const FrameParams &fp = fp_in;
     if ((rc = wf_prepare(s, sl, fp, wf)) != ERT_OK) return rc;
     cudaStream_t st = sl.stream;
+    FrameParams fps = fp;                           // shadow kernels count into the second counter set
+    fps.counters = fp.counters + CNT_N;
+    size_t n_ticks = 0;
+    sl.tick_class.clear();
+    auto tick = [&](int cls) -> int {              // cls < 0: the opening event
+        if (!timed) return ERT_OK;
+        if (n_ticks == sl.ticks.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            sl.ticks.push_back(e);
+        }
+        CU(cudaEventRecord(sl.ticks[n_ticks++], st));
+        if (cls >= 0) sl.tick_class.push_back(cls);
+        return ERT_OK;
+    };
+#define TICK(cls) do { if ((rc = tick(cls)) != ERT_OK) return rc; } while (0)
+    TICK(-1);
     const DevScene &d = s->dev;
     CU(cudaMemsetAsync(wf.ctr, 0, (size_t)fp.depth * kWfCtr * sizeof(unsigned int), st));
     CU(cudaMemsetAsync(wf.C, 0, (size_t)wf.n_pad * 3 * sizeof(double), st));
@@ -569,6 +591,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorte
         else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         else wf_trace_path_refill<COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         n++;
+        TICK(0);
         WF_CHECK("wf_trace_path");
         if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
         if (b == 0) {
@@ -584,18 +607,23 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp, bool unsorte
             n += 3;
         }
         n++;
+        TICK(2);
         WF_CHECK("wf_emit_hits / wf_bin_*");
-        if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fp, wf, b);
+        if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
+        else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
+        TICK(1);
         WF_CHECK("wf_trace_shadow");
         wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
         n += 2;
+        TICK(2);
         WF_CHECK("wf_shade");
     }
     wf_finalize<<<s->wf_grid[3], kWfThreads, 0, st>>>(fp, wf);
     n++;
+    TICK(2);
     CU(cudaGetLastError());
 #undef WF_CHECK
+#undef TICK
     *launches = n;
     return ERT_OK;
 }
@@ -611,11 +639,25 @@ int finish_slot(ert_scene *s, Slot &sl)
     cudaEventElapsedTime(&t, sl.ev0, sl.ev2);
     sl.stats.kernel_ms = k;
     sl.stats.total_ms = t;
-    sl.stats.rays = sl.counters_host[CNT_RAYS];
-    sl.stats.sphere_filter_tests = sl.counters_host[CNT_FILTER];
-    sl.stats.box_tests = sl.counters_host[CNT_BOX];
-    sl.stats.exact_sphere_tests = sl.counters_host[CNT_EXACT_SPH];
-    sl.stats.exact_other_tests = sl.counters_host[CNT_EXACT_OTHER];
+    const unsigned long long *c0 = sl.counters_host, *c1 = sl.counters_host + CNT_N;
+    sl.stats.rays = c0[CNT_RAYS] + c1[CNT_RAYS];
+    sl.stats.sphere_filter_tests = c0[CNT_FILTER] + c1[CNT_FILTER];
+    sl.stats.box_tests = c0[CNT_BOX] + c1[CNT_BOX];
+    sl.stats.exact_sphere_tests = c0[CNT_EXACT_SPH] + c1[CNT_EXACT_SPH];
+    sl.stats.exact_other_tests = c0[CNT_EXACT_OTHER] + c1[CNT_EXACT_OTHER];
+    sl.stats.path_box_tests = c0[CNT_BOX]; sl.stats.path_filter_tests = c0[CNT_FILTER];
+    sl.stats.shadow_box_tests = c1[CNT_BOX]; sl.stats.shadow_filter_tests = c1[CNT_FILTER];
+    // per-class device time of the wavefront launches (ERT_FLAG_TIME_KERNELS)
+    for (size_t i = 0; i + 1 < sl.tick_class.size() + 1 && i < sl.tick_class.size(); i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sl.ticks[i], sl.ticks[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        switch (sl.tick_class[i]) {
+        case 0: sl.stats.path_ms += ms; sl.stats.path_launches++; break;
+        case 1: sl.stats.shadow_ms += ms; sl.stats.shadow_launches++; break;
+        default: sl.stats.other_ms += ms; break;
+        }
+    }
+    sl.tick_class.clear();
     (void)s;
     return ERT_OK;
 }
@@ -754,14 +796,15 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
     sl.stats.pixels = (uint64_t)fp.local_rows * (uint64_t)p.width;
     sl.stats.h2d_bytes = sizeof(DevScene) + sizeof(FrameParams);   // kernel parameters of this frame
 
-    CU(cudaMemsetAsync(sl.counters_dev, 0, CNT_N * sizeof(unsigned long long), sl.stream));
+    CU(cudaMemsetAsync(sl.counters_dev, 0, kCounterSets * CNT_N * sizeof(unsigned long long), sl.stream));
     CU(cudaEventRecord(sl.ev0, sl.stream));
     if (fp.local_rows > 0 && accel == ERT_ACCEL_BVH && fp.depth > 0) {
         uint64_t n = 0;
         const bool unsorted = (p.flags & ERT_FLAG_WF_UNSORTED) != 0;
         const bool no_grid = (p.flags & ERT_FLAG_NO_LIGHT_GRID) != 0;
-        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, &n)
-                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, &n);
+        const bool timed = (p.flags & ERT_FLAG_TIME_KERNELS) != 0;
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, timed, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, timed, &n);
         if (rc != ERT_OK) return rc;
         sl.stats.gpu_launches = n;
     } else if (fp.local_rows > 0) {
@@ -772,8 +815,8 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
         sl.stats.gpu_launches = 1;
     }
     CU(cudaEventRecord(sl.ev1, sl.stream));
-    CU(cudaMemcpyAsync(sl.counters_host, sl.counters_dev, CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                       sl.stream));
+    CU(cudaMemcpyAsync(sl.counters_host, sl.counters_dev, kCounterSets * CNT_N * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, sl.stream));
     sl.has_frame = true;
     sl.busy = true;
     if (host_frame && fp.local_rows > 0) {

@@ -87,6 +87,7 @@ struct FrameParams {
 };
 
 enum Counter : int { CNT_RAYS = 0, CNT_FILTER = 1, CNT_BOX = 2, CNT_EXACT_SPH = 3, CNT_EXACT_OTHER = 4, CNT_N = 8 };
+constexpr int kCounterSets = 2;      // [0]: megakernels and wf_trace_path*, [1]: wf_trace_shadow
 
 // ------------------------------------------------------------------ FP64 literal algebra
 struct d3 { double x, y, z; };

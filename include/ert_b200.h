@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERT_ABI_VERSION 1
+#define ERT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ERT_API __attribute__((visibility("default")))
@@ -121,6 +121,7 @@ typedef struct ert_scene_desc {
 #define ERT_ACCEL_BVH_MEGAKERNEL 4  /* same BVH, one launch, per-pixel state machine (kept as a cross-check) */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
+#define ERT_FLAG_TIME_KERNELS  8u  /* ERT_ACCEL_BVH: CUDA events around every launch; fills the *_ms split of ert_stats */
 #define ERT_FLAG_NO_LIGHT_GRID 4u /* ERT_ACCEL_BVH: shadow rays walk the BVH even for lights that have a
                                    * direction grid (A/B switch; same frame) */
 #define ERT_FLAG_WF_UNSORTED  2u  /* ERT_ACCEL_BVH: skip the binning of hits by location (A/B switch; the
@@ -157,6 +158,12 @@ typedef struct ert_stats {
     uint64_t exact_other_tests;     /* FP64 plane/triangle evaluations */
     int32_t accel_used;             /* ERT_ACCEL_* actually run */
     int32_t reserved;
+    /* wavefront form (ERT_ACCEL_BVH) only.  Test counters split by kernel class (with
+     * ERT_FLAG_COUNT_TESTS) and device time by kernel class (with ERT_FLAG_TIME_KERNELS). */
+    uint64_t path_box_tests, path_filter_tests;       /* wf_trace_path*: BVH walks of path rays */
+    uint64_t shadow_box_tests, shadow_filter_tests;   /* wf_trace_shadow: direction grids / BVH walks */
+    double path_ms, shadow_ms, other_ms;              /* other: hit emission, binning, shading, finalize */
+    uint64_t path_launches, shadow_launches;
 } ert_stats;
 
 typedef struct ert_scene ert_scene;     /* opaque: device-resident flattened scene */

@@ -337,12 +337,14 @@ def test_wavefront_binned_queues_render_the_same_frame(gpu):
     flat = sc.synthetic_scene("c3")
     dev = flat.upload(0)
     w, h, depth = 640, 360, 5
-    a, sa = dev.render(w, h, depth, fmt="f64", accel="bvh")
-    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_WF_UNSORTED)
+    # hits are binned when shadow rays walk the BVH (here: direction grids switched off)
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_NO_LIGHT_GRID)
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_NO_LIGHT_GRID | _lib.FLAG_WF_UNSORTED)
     c, sc_ = dev.render(w, h, depth, fmt="f64", accel="bvh_mega")
-    assert np.array_equal(a, b) and np.array_equal(a, c)
-    assert sa["rays"] == sb["rays"] == sc_["rays"]
-    assert sa["gpu_launches"] > sb["gpu_launches"] > sc_["gpu_launches"] == 1
+    e, se = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, e)
+    assert sa["rays"] == sb["rays"] == sc_["rays"] == se["rays"]
+    assert sa["gpu_launches"] > sb["gpu_launches"] == se["gpu_launches"] > sc_["gpu_launches"] == 1
     # instrumented run: same frame, counters filled
     d, sd = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
     assert np.array_equal(a, d) and sd["box_tests"] > 0 and sd["sphere_filter_tests"] > 0
@@ -394,3 +396,60 @@ def test_wavefront_row_band_parts_assemble_the_frame(gpu):
         rays += sp["rays"]
     assert np.array_equal(out, full) and rays == st["rays"]
     dev.close()
+
+
+def test_light_grids_answer_shadow_queries_like_the_bvh(gpu):
+    """Direction grids (light_grid.cpp) vs BVH walks vs the unfiltered FP64 scan: same frame."""
+    flat = sc.synthetic_scene("c3")
+    dev = flat.upload(0)
+    w, h, depth = 480, 270, 5
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS | _lib.FLAG_NO_LIGHT_GRID)
+    c, _ = dev.render(w, h, depth, fmt="f64", accel="exact")
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert sa["rays"] == sb["rays"]
+    assert sa["shadow_box_tests"] == 0 < sb["shadow_box_tests"]        # no walk when the light has a grid
+    assert 0 < sa["shadow_filter_tests"] and 0 < sa["path_box_tests"] == sb["path_box_tests"]
+    t, st = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_TIME_KERNELS)
+    assert np.array_equal(a, t)
+    assert st["path_launches"] == depth and st["shadow_launches"] == depth
+    assert 0 < st["path_ms"] + st["shadow_ms"] + st["other_ms"] <= st["kernel_ms"] * 1.05
+    dev.close()
+
+
+def test_more_lights_than_direction_grids(gpu):
+    """Lights past the first kMaxLightGrids (8) send their shadow rays through the BVH."""
+    n_lights = 11
+    flat = sc.synthetic_scene("c3", n_spheres=1500)
+    lights = np.zeros(n_lights, dtype=_lib.LIGHT_DT)
+    for k in range(n_lights):
+        lights[k]['diffuse_colour'] = (0.05 * k, 0.3, 0.6 - 0.04 * k)
+        lights[k]['location'] = (7.0 * k - 35, -25 + 3 * k, 2.0 * k)
+        lights[k]['specular_colour'] = (1, 1, 1)
+        lights[k]['order'] = k
+    flat.spheres['order'] = np.arange(n_lights, n_lights + len(flat.spheres), dtype=np.int32)
+    flat.planes['order'] = n_lights + len(flat.spheres)
+    flat.lights = lights
+    dev = flat.upload(0)
+    w, h, depth = 80, 45, 3
+    ref, ref_rays, _ = oracle_frame(flat, w, h, depth)
+    frame, st = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
+    assert_double_parity(frame, ref)
+    assert np.array_equal(quantise(frame), quantise(ref)) and st["rays"] == ref_rays
+    assert st["shadow_box_tests"] > 0
+    dev.close()
+
+
+def test_light_inside_a_sphere_and_on_a_surface(gpu):
+    """The `always` list of a direction grid: a light inside a sphere, and one touching another."""
+    spheres = [('sphere', 3.0, ('vector', 0, 0, 12), mat((0.2, 0.6, 1.0), 20, 1, 0.4))]
+    rng = np.random.default_rng(3)
+    for i in range(80):
+        c = rng.uniform(-8, 8, 3) + (0, 0, 14)
+        spheres.append(('sphere', float(rng.uniform(0.3, 0.9)), ('vector',) + tuple(c.tolist()),
+                        mat(tuple(rng.uniform(0, 1, 3).tolist()), 4, 0.5, 0.3)))
+    lights = [('point_light', ('colour', 1, 1, 1), ('vector', 0.5, -0.5, 11), ('colour', 1, 1, 1)),     # inside sphere 0
+              ('point_light', ('colour', 1, 0.5, 0.2), ('vector', 0, -3, 12), ('colour', 1, 1, 1)),    # on its surface
+              ('point_light', ('colour', 0.3, 1, 0.4), ('vector', -12, -9, 2), ('colour', 1, 1, 1))]
+    scene = [CAM] + lights + spheres + [('plane', ('vector', 0, -1, 0), 6, mat((1, 1, 1), 1, 0, 0.2))]
+    check_scene(scene, 96, 72, 4, accels=("exact", "bvh", "bvh_mega"))
