@@ -518,15 +518,26 @@ constexpr unsigned int kWfChunk = ERT_WF_CHUNK;
 constexpr int kOccCache = ERT_WF_OCC_CACHE;      // recent occluders a warp remembers (wf_trace_shadow)
 static_assert(kWfChunk % 32 == 0, "chunks are whole batches");
 
+// Chunk length for a queue of `total` entries: kWfChunk, but short queues (a band of a frame
+// split over several GPUs, late bounces) are cut finer so that every warp of the grid gets
+// several chunks and the tail of the launch stays short.
+__device__ __forceinline__ unsigned int chunk_len(unsigned long long total)
+{
+    const unsigned long long warps = (unsigned long long)gridDim.x * (kWfThreads / 32);
+    unsigned long long c = total / (warps * 8);
+    c &= ~31ull;
+    return c < 32 ? 32u : (c > kWfChunk ? kWfChunk : (unsigned int)c);
+}
 __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned long long total, int lane,
                                            unsigned long long &begin, unsigned long long &end)
 {
+    const unsigned int len = chunk_len(total);
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kWfChunk);
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)len);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= total) return false;
     begin = base;
-    end = base + kWfChunk < total ? base + kWfChunk : total;
+    end = base + len < total ? base + len : total;
     return true;
 }
 

@@ -1,9 +1,9 @@
 #!/bin/bash
-# launch list + full captures of the wavefront traversal kernels on C4
+# ncu launch list (one steady-state frame) + full captures of the wavefront traversal kernels on C4
 mkdir -p gpurun_out
 CMD="python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 24 --csv --log-file gpurun_out/wf_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 90 -c 44 --csv --log-file gpurun_out/wf_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:wf_trace -s 10 -c 5 -o gpurun_out/prof_wf $CMD > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out | tail -8
+ncu --set full --clock-control none --import-source on -k regex:wf_trace -s 10 -c 10 -o gpurun_out/prof_wf $CMD > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | tail -4
