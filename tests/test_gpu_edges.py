@@ -323,6 +323,10 @@ def test_c4_full_4k_bvh_equals_linear_scan_and_oracle_samples(gpu):
     ob, tb = dev.trace_rays(rays, accel="bvh")
     ol, tl = dev.trace_rays(rays, accel="linear")
     assert np.array_equal(ob, ol) and np.array_equal(tb, tl)
+    # shadow rays through the lights' direction grids == shadow rays through the BVH, whole 4K frame
+    walk, sw = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_NO_LIGHT_GRID)
+    assert np.array_equal(walk, full) and sw["rays"] == st["rays"]
+    del walk
     # the CPU oracle on a few pixels (each costs ~16 rays x 1M spheres)
     xs = np.array([400, 1900, 3000, 1200], dtype=np.int32)
     ys = np.array([300, 1500, 900, 2000], dtype=np.int32)
