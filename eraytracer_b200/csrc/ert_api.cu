@@ -494,7 +494,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     // lit bytes | sort histogram + block sums
     size_t off = 0;
     size_t o_dbl = off; off += align_up(n_pad * 11 * sizeof(double), 256);
-    size_t o_rec = off; off += align_up(n_pad * 2 * sizeof(HitRec), 256);
+    size_t o_rec = off; off += align_up(n_pad * 2 * (sizeof(HitHead) + sizeof(HitTail)), 256);
     size_t o_int = off; off += align_up(n_pad * 4 * sizeof(int), 256);
     size_t o_lit = off; off += align_up(n_pad * L, 256);
     size_t o_hist = off; off += align_up(((size_t)kSortCells + kSortBlocks) * sizeof(unsigned int), 256);
@@ -521,7 +521,8 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     wf.n_pad = (int)n_pad;
     wf.tiles_x = tiles_x;
     wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.res_t = d + 10 * n_pad;
-    wf.hits = (HitRec *)(base + o_rec); wf.raw_hits = wf.hits + n_pad;
+    wf.hit_head = (HitHead *)(base + o_rec); wf.raw_head = wf.hit_head + n_pad;
+    wf.hit_tail = (HitTail *)(wf.raw_head + n_pad); wf.raw_tail = wf.hit_tail + n_pad;
     wf.q_pid = i; wf.res_hit = (int2 *)(i + n_pad); wf.r_key = (unsigned int *)(i + 3 * n_pad);
     wf.lit = base + o_lit;
     wf.hist = (unsigned int *)(base + o_hist);

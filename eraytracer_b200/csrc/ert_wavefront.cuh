@@ -35,17 +35,19 @@
 
 namespace ert {
 
-// One hit of a path ray.  96 bytes, laid out so that each consumer touches whole 32-byte
-// sectors: the shadow stage needs only the first one.
-struct alignas(16) HitRec {
+// One hit of a path ray, in two records: the shadow stage streams only the 32-byte heads
+// (dense, every fetched byte used), the shade stage reads both.
+struct alignas(32) HitHead {
     double P[3];                // hit location
     int obj, order;             // object code, list position
+};
+struct alignas(32) HitTail {
     double N[3];                // normal
     int pid, pad0;              // pixel of the path
     double D[3];                // direction of the ray that hit
     double pad1;
 };
-static_assert(sizeof(HitRec) == 96, "HitRec must be 96 bytes");
+static_assert(sizeof(HitHead) == 32 && sizeof(HitTail) == 64, "hit records are 32 + 64 bytes");
 
 struct WfBuf {
     int n_pad;                  // pixels of this part padded to whole 8x4 tiles: tiles * 32
@@ -56,8 +58,10 @@ struct WfBuf {
     double *q_ray;              // [6][n_pad] origin xyz, direction xyz
     double *res_t;              // nearest hit of each path ray: Distance,
     int2 *res_hit;              //   (object code or -1, list position)
-    HitRec *hits;               // hit queue the shadow and shade stages read
-    HitRec *raw_hits;           // hit queue in arrival order (bounces >= 1, before binning)
+    HitHead *hit_head;          // hit queue the shadow and shade stages read
+    HitTail *hit_tail;
+    HitHead *raw_head;          // hit queue in arrival order (before binning, when hits are binned)
+    HitTail *raw_tail;
     unsigned int *r_key;        // cell of each raw hit (Morton order)
     unsigned char *lit;         // [n_lights][n_pad] shadow factor of (light, hit)
     unsigned int *ctr;          // [depth][kWfCtr] queue lengths and work cursors
@@ -441,10 +445,12 @@ __global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_consta
     for (size_t h = (size_t)blockIdx.x * kWfThreads + threadIdx.x; h < n_hits; h += (size_t)gridDim.x * kWfThreads) {
         unsigned int key = wf.r_key[h];
         size_t s = (size_t)atomicAdd(wf.hist + key, 1u) + wf.sums[key / kSortScanBlock];
-        const uint4 *src = reinterpret_cast<const uint4 *>(wf.raw_hits + h);
-        uint4 *dst = reinterpret_cast<uint4 *>(wf.hits + s);
-        uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3], r4 = src[4], r5 = src[5];
-        dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3; dst[4] = r4; dst[5] = r5;
+        const uint4 *sh = reinterpret_cast<const uint4 *>(wf.raw_head + h);
+        const uint4 *st = reinterpret_cast<const uint4 *>(wf.raw_tail + h);
+        uint4 r0 = sh[0], r1 = sh[1], r2 = st[0], r3 = st[1], r4 = st[2], r5 = st[3];
+        uint4 *dh = reinterpret_cast<uint4 *>(wf.hit_head + s);
+        uint4 *dt = reinterpret_cast<uint4 *>(wf.hit_tail + s);
+        dh[0] = r0; dh[1] = r1; dt[0] = r2; dt[1] = r3; dt[2] = r4; dt[3] = r5;
     }
 }
 
@@ -481,10 +487,10 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
         ldg256(lg.cand + e, c);
         if (c[5] > cull0) break;                         // this and all later candidates lie beyond the target
         const float4 fs = make_float4(c[0], c[1], c[2], c[3]);
+        const int sph = __float_as_int(c[4]);
         float fb, fv;
         TALLY(filter);
         if (!filter_stage1(f, fs, fb, fv) || !filter_stage2(f, fs, fb, fv, cull0)) continue;
-        const int sph = __float_as_int(c[4]);
         if (obj_code(OBJ_SPHERE, sph) == target) continue;
         double th;
         TALLY(exact_sph);
@@ -708,7 +714,8 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
     const int lane = threadIdx.x & 31;
     const unsigned int warp = (blockIdx.x * kWfThreads + threadIdx.x) >> 5;
     const unsigned int n_warps = (gridDim.x * kWfThreads) >> 5;
-    HitRec *out = SORT ? wf.raw_hits : wf.hits;
+    HitHead *out_head = SORT ? wf.raw_head : wf.hit_head;
+    HitTail *out_tail = SORT ? wf.raw_tail : wf.hit_tail;
     for (unsigned long long base = (unsigned long long)warp * 32; base < n; base += (unsigned long long)n_warps * 32) {
         unsigned int i = (unsigned int)base + lane;
         int2 r = make_int2(-1, 0);
@@ -728,14 +735,19 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
             d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
             d3 N = hit_normal(sc, r.x, P);
             size_t s = slot0 + rank_in(m, lane);
-            HitRec rec;
-            rec.P[0] = P.x; rec.P[1] = P.y; rec.P[2] = P.z; rec.obj = r.x; rec.order = r.y;
-            rec.N[0] = N.x; rec.N[1] = N.y; rec.N[2] = N.z; rec.pid = pid; rec.pad0 = 0;
-            rec.D[0] = D.x; rec.D[1] = D.y; rec.D[2] = D.z; rec.pad1 = 0.0;
-            const uint4 *src = reinterpret_cast<const uint4 *>(&rec);
-            uint4 *dst = reinterpret_cast<uint4 *>(out + s);
-#pragma unroll
-            for (int k = 0; k < 6; k++) dst[k] = src[k];
+            HitHead hh;
+            HitTail ht;
+            hh.P[0] = P.x; hh.P[1] = P.y; hh.P[2] = P.z; hh.obj = r.x; hh.order = r.y;
+            ht.N[0] = N.x; ht.N[1] = N.y; ht.N[2] = N.z; ht.pid = pid; ht.pad0 = 0;
+            ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.pad1 = 0.0;
+            {
+                const uint4 *sh = reinterpret_cast<const uint4 *>(&hh);
+                const uint4 *st = reinterpret_cast<const uint4 *>(&ht);
+                uint4 *dh = reinterpret_cast<uint4 *>(out_head + s);
+                uint4 *dt = reinterpret_cast<uint4 *>(out_tail + s);
+                dh[0] = sh[0]; dh[1] = sh[1];
+                dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+            }
             if constexpr (SORT) {
                 unsigned int key = sort_cell(sc, P);
                 wf.r_key[s] = key;
@@ -795,7 +807,7 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             rays++;
             bool lit = false;
             {
-                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hits + h);
+                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
                 d3 P = mk(r0.x, r0.y, r0.z);
                 const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
                 const int order = (int)(__double_as_longlong(r0.w) >> 32);
@@ -900,16 +912,21 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
         int pid = 0;
         d3 P = mk(0, 0, 0), N = P, D = P;
         if (valid) {
-            HitRec rec;
-            const uint4 *src = reinterpret_cast<const uint4 *>(wf.hits + h);
-            uint4 *dst = reinterpret_cast<uint4 *>(&rec);
-#pragma unroll
-            for (int k = 0; k < 6; k++) dst[k] = src[k];
-            pid = rec.pid;
-            P = mk(rec.P[0], rec.P[1], rec.P[2]);
-            N = mk(rec.N[0], rec.N[1], rec.N[2]);
-            D = mk(rec.D[0], rec.D[1], rec.D[2]);
-            const double *mat = material_ptr(sc, rec.obj);
+            HitHead hh;
+            HitTail ht;
+            {
+                const uint4 *sh = reinterpret_cast<const uint4 *>(wf.hit_head + h);
+                const uint4 *st = reinterpret_cast<const uint4 *>(wf.hit_tail + h);
+                uint4 *dh = reinterpret_cast<uint4 *>(&hh);
+                uint4 *dt = reinterpret_cast<uint4 *>(&ht);
+                dh[0] = sh[0]; dh[1] = sh[1];
+                dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+            }
+            pid = ht.pid;
+            P = mk(hh.P[0], hh.P[1], hh.P[2]);
+            N = mk(ht.N[0], ht.N[1], ht.N[2]);
+            D = mk(ht.D[0], ht.D[1], ht.D[2]);
+            const double *mat = material_ptr(sc, hh.obj);
             d3 S = mk(0.0, 0.0, 0.0);
             for (int l = 0; l < L; l++) {
                 if (wf.lit[(size_t)l * np + h]) S = vadd(S, light_term(sc.lights + 9 * (size_t)l, mat, P, N, D));

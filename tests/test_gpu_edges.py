@@ -457,3 +457,27 @@ def test_light_inside_a_sphere_and_on_a_surface(gpu):
               ('point_light', ('colour', 0.3, 1, 0.4), ('vector', -12, -9, 2), ('colour', 1, 1, 1))]
     scene = [CAM] + lights + spheres + [('plane', ('vector', 0, -1, 0), 6, mat((1, 1, 1), 1, 0, 0.2))]
     check_scene(scene, 96, 72, 4, accels=("exact", "bvh", "bvh_mega"))
+
+
+@pytest.mark.parametrize("n,expect", [(16, "exact"), (17, "linear"), (63, "linear"), (64, "linear"), (192, "linear"),
+                                      (193, "bvh")])
+def test_auto_strategy_thresholds(gpu, n, expect):
+    """AUTO switches strategy at 16/17 and 192/193 spheres; direction grids start at 64.  Same frame on
+    both sides of every threshold."""
+    rng = np.random.default_rng(n)
+    spheres = [('sphere', float(rng.uniform(0.2, 0.9)), ('vector', float(rng.uniform(-7, 7)), float(rng.uniform(-5, 4)),
+                float(rng.uniform(4, 22))), mat(tuple(float(x) for x in rng.uniform(0, 1, 3)), 4, 0.5, 0.4))
+               for _ in range(n)]
+    scene = [CAM, L1, L2] + spheres + [('plane', ('vector', 0, -1, 0), 5, mat((1, 1, 1), 1, 0, 0.2))]
+    flat = sc.flatten(scene)
+    dev = flat.upload(0)
+    w, h, depth = 72, 54, 4
+    ref, ref_rays, _ = oracle_frame(flat, w, h, depth)
+    frame, st = dev.render(w, h, depth, fmt="f64", accel="auto")
+    assert st["accel_used"] == expect
+    assert_double_parity(frame, ref)
+    assert np.array_equal(quantise(frame), quantise(ref)) and st["rays"] == ref_rays
+    wf, sw = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
+    assert np.array_equal(wf, frame) and sw["rays"] == ref_rays
+    assert (sw["shadow_box_tests"] == 0) == (n >= 64)       # direction grids from 64 spheres on
+    dev.close()
