@@ -270,6 +270,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     common = dict(fmt=fmt, accel=accel, band_rows=band_rows, n_parts=n_parts, part=rank)
     peak = _lib.fp32_peak(local_rank)
+    peak_rrr = _lib.fp32_peak_rrr(local_rank)
 
     # warm-up through the full end-to-end path
     for i in range(max(args.warmup, 0)):
@@ -363,10 +364,11 @@ def gpu_arm(args, rank, world, local_rank):
         # the path rays (wf_trace_path / wf_trace_path_refill); other accels are one kernel per frame.
         k_s = (kernel_ms / steps) * 1e-3
         frame_lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10
-        wavefront = counted["accel_used"] == "bvh" and split["path_launches"] > 0
+        wavefront = split["path_launches"] > 0
+        dom = "path" if split["path_ms"] >= split["shadow_ms"] else "shadow"
         if wavefront:
-            lane_instr = counted["path_box_tests"] * 6 + counted["path_filter_tests"] * 10
-            dom_s = (split["path_ms"] / steps) * 1e-3
+            lane_instr = counted[dom + "_box_tests"] * 6 + counted[dom + "_filter_tests"] * 10
+            dom_s = (split[dom + "_ms"] / steps) * 1e-3
         else:
             lane_instr, dom_s = frame_lane_instr, k_s
         achieved = lane_instr / dom_s
@@ -407,24 +409,35 @@ def gpu_arm(args, rank, world, local_rank):
             "roofline": {
                 "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"bvh": "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
-                           "bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
-                           "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?"),
+                "kernel": ({("bvh", "path"): "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
+                            ("bvh", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
+                            ("linear", "path"): "wf_scan_path (brute-force filter scan of the path rays)",
+                            ("linear", "shadow"): "wf_scan_shadow (brute-force filter scan of the shadow rays)"}
+                           .get((counted["accel_used"], dom), "?") if wavefront else
+                           {"bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
+                            "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?")),
                 "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test of the "
                               "named kernels (counts from an instrumented run of the same frame on rank 0), divided "
                               "by their CUDA-event time inside the timed steps",
-                "launches_per_step": (split["path_launches"] / steps) if wavefront else 1,
-                "avg_launch_ms": (split["path_ms"] / max(split["path_launches"], 1)) if wavefront else kernel_ms / steps,
-                "share_of_step": (split["path_ms"] / kernel_ms) if wavefront else 1.0,
-                "box_tests": int(counted["path_box_tests"] if wavefront else counted["box_tests"]),
-                "sphere_filter_tests": int(counted["path_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
+                "launches_per_step": (split[dom + "_launches"] / steps) if wavefront else 1,
+                "avg_launch_ms": (split[dom + "_ms"] / max(split[dom + "_launches"], 1)) if wavefront else kernel_ms / steps,
+                "share_of_step": (split[dom + "_ms"] / kernel_ms) if wavefront else 1.0,
+                "box_tests": int(counted[dom + "_box_tests"] if wavefront else counted["box_tests"]),
+                "sphere_filter_tests": int(counted[dom + "_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
                 "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
                 "frame": {"lane_instr": int(frame_lane_instr), "frac": frame_lane_instr / k_s / peak,
                           "box_tests": int(counted["box_tests"]),
                           "sphere_filter_tests": int(counted["sphere_filter_tests"]),
+                          "class_frac": {c: ((counted[c + "_box_tests"] * 6 + counted[c + "_filter_tests"] * 10)
+                                             / max(split[c + "_ms"] / steps * 1e-3, 1e-12) / peak)
+                                         for c in ("path", "shadow")} if wavefront else None,
                           "ms": {"path": split["path_ms"] / steps, "shadow": split["shadow_ms"] / steps,
                                  "other": split["other_ms"] / steps, "all": kernel_ms / steps}},
-                "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry)",
+                "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry); "
+                               "FFMA with an immediate addend, the fastest form",
+                "peak_rrr": peak_rrr / 1e9, "frac_of_peak_rrr": achieved / peak_rrr,
+                "peak_rrr_source": "the same loop with three register operands per FFMA, the form the intersection "
+                                   "kernels issue",
                 "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
             },
         }

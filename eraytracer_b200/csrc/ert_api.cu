@@ -19,6 +19,10 @@
 #include "ert_device.cuh"
 #include "ert_wavefront.cuh"
 
+// ERT_ACCEL_LINEAR: scenes up to this many spheres stay in the single-launch tiled kernel (one resident
+// tile, no queue traffic); larger ones run the wavefront with the brute-force scan kernels.
+constexpr int kWfScanFrom = 192;
+
 #ifndef ERT_WF_REFILL_FROM
 #define ERT_WF_REFILL_FROM 2        /* first bounce whose path rays use the refilling kernel */
 #endif
@@ -96,6 +100,7 @@ struct Slot {
 struct ert_scene {
     int device = 0;
     int wf_grid[4] = {0, 0, 0, 0};     // persistent grid sizes: path(first), path, shadow, shade
+    int wf_grid_scan = 0;              // brute-force scan kernels (2 blocks per SM)
     HostScene host;
     DevScene dev{};
     std::vector<void *> allocs;
@@ -373,6 +378,14 @@ int upload_scene(ert_scene *s)
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
         s->wf_grid[3] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaFuncSetAttribute(wf_scan_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_scan_path<false, false>, kWfThreads, kScanSmem));
+        s->wf_grid_scan = prop.multiProcessorCount * std::max(nb, 1);
     }
     return ERT_OK;
 }
@@ -533,7 +546,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
 
 template <bool COUNT>
 int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unsorted, bool no_grid, bool timed,
-                     uint64_t *launches)
+                     bool scan, uint64_t *launches)
 {
     WfBuf wf{};
     int rc;
@@ -587,8 +600,10 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             CU(cudaStreamSynchronize(st));
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
-        const bool sort = b >= 1 && !no_sort;
-        if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        const bool sort = b >= 1 && !no_sort && !scan;
+        if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
+        else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
+        else if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
         else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         else wf_trace_path_refill<COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         n++;
@@ -610,7 +625,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         n++;
         TICK(2);
         WF_CHECK("wf_emit_hits / wf_bin_*");
-        if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
+        if (scan) wf_scan_shadow<COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fps, wf, b);
+        else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         TICK(1);
         WF_CHECK("wf_trace_shadow");
@@ -799,13 +815,15 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
 
     CU(cudaMemsetAsync(sl.counters_dev, 0, kCounterSets * CNT_N * sizeof(unsigned long long), sl.stream));
     CU(cudaEventRecord(sl.ev0, sl.stream));
-    if (fp.local_rows > 0 && accel == ERT_ACCEL_BVH && fp.depth > 0) {
+    // the wavefront serves the BVH strategy and, past one resident tile of spheres, the brute-force scan
+    const bool wf_scan = accel == ERT_ACCEL_LINEAR && scene->host.n_spheres > kWfScanFrom;
+    if (fp.local_rows > 0 && (accel == ERT_ACCEL_BVH || wf_scan) && fp.depth > 0) {
         uint64_t n = 0;
         const bool unsorted = (p.flags & ERT_FLAG_WF_UNSORTED) != 0;
         const bool no_grid = (p.flags & ERT_FLAG_NO_LIGHT_GRID) != 0;
         const bool timed = (p.flags & ERT_FLAG_TIME_KERNELS) != 0;
-        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, timed, &n)
-                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, timed, &n);
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, &n);
         if (rc != ERT_OK) return rc;
         sl.stats.gpu_launches = n;
     } else if (fp.local_rows > 0) {
@@ -980,6 +998,43 @@ int ert_fp32_peak(int device, double *lane_instr_per_s)
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(out);
+    *lane_instr_per_s = best;
+    return ERT_OK;
+}
+
+int ert_fp32_peak_rrr(int device, double *lane_instr_per_s)
+{
+    if (!lane_instr_per_s) return fail(ERT_ERR_BADARG, "out is NULL");
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8;
+    float *out = nullptr, *in = nullptr;
+    CU(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(float)));
+    CU(cudaMalloc(&in, 8 * sizeof(float)));
+    const float host_in[8] = {1.0f, 0.9999f, 0.99991f, 0.0001f, 0.00011f, 0, 0, 0};
+    CU(cudaMemcpy(in, host_in, sizeof host_in, cudaMemcpyHostToDevice));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const int iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(a));
+        fp32_peak_rrr_kernel<<<blocks, 256>>>(out, iters, in);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double rate = (double)blocks * 256.0 * iters * kPeakFfmaPerIter / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, rate);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    cudaFree(in);
     *lane_instr_per_s = best;
     return ERT_OK;
 }

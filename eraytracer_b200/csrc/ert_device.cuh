@@ -877,6 +877,26 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
 }
 constexpr int kPeakFfmaPerIter = 16 * 8;
 
+// The same loop with three REGISTER operands per FFMA (multiplier and addend are run-time values):
+// the form the intersection kernels actually issue (box planes, sphere centres and ray constants all
+// live in registers).
+__global__ void __launch_bounds__(256) fp32_peak_rrr_kernel(float *out, int iters, const float *__restrict__ in)
+{
+    float a0 = in[0] + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m0 = in[1], m1 = in[2], c0 = in[3], c1 = in[4];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            a0 = __fmaf_rn(a0, m0, c0); a1 = __fmaf_rn(a1, m1, c1); a2 = __fmaf_rn(a2, m0, c1); a3 = __fmaf_rn(a3, m1, c0);
+            a4 = __fmaf_rn(a4, m0, c0); a5 = __fmaf_rn(a5, m1, c1); a6 = __fmaf_rn(a6, m0, c1); a7 = __fmaf_rn(a7, m1, c0);
+        }
+    }
+    float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void l2_flush_kernel(uint4 *buf, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -892,6 +892,257 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
+// ------------------------------------------------------------------ brute-force scan (ERT_ACCEL_LINEAR)
+// The reference's linear scan (erl:300-346) as a wavefront: same queues, same set-up, but every
+// ray tests EVERY sphere — the FP32 filter over tiles of the list-ordered filter array, streamed
+// global -> shared by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) into a double buffer
+// that a block of 256 rays shares.  This is the kernel the FP32-issue roofline is about: 10
+// FP32-pipe instructions + 1 compare + 1/UNROLL of a broadcast LDS.128 per (ray, sphere).
+// A block takes 256 consecutive queue entries at a time (one ray per thread).
+#ifndef ERT_SCAN_TILE
+#define ERT_SCAN_TILE 2048
+#endif
+#ifndef ERT_SCAN_MINBLOCKS
+#define ERT_SCAN_MINBLOCKS 2
+#endif
+constexpr int kScanTile = ERT_SCAN_TILE;                  // filter spheres per buffer (16 B each)
+static_assert(kScanTile % 8 == 0, "tiles are whole groups");
+constexpr int kScanSmem = 2 * kScanTile * 16;             // dynamic shared memory of the scan kernels
+
+struct ScanPipe {
+    float4 *tiles;
+    uint64_t *bars;
+    uint32_t phase_bits;
+};
+
+// Streams all tiles once; `body(tile, count, base_index)` runs for every tile while `active`.
+// Every thread of the block must call this together.  ANY: the block stops streaming once no thread is active.
+template <class Body>
+__device__ __forceinline__ void scan_all_tiles(const DevScene &sc, ScanPipe &pp, bool &active, Body body)
+{
+    const int n = sc.n_spheres;
+    const int n_tiles = (n + kScanTile - 1) / kScanTile;
+    if (threadIdx.x == 0 && n_tiles > 0) {
+        const int cnt = min(kScanTile, n);
+        mbar_expect_tx(&pp.bars[0], cnt * 16u);
+        bulk_g2s(pp.tiles, sc.sph_filter, cnt * 16u, &pp.bars[0]);
+    }
+    for (int t = 0; t < n_tiles; t++) {
+        const int buf = t & 1;
+        bool more = true;
+        if (t + 1 < n_tiles) {
+            more = __syncthreads_or(active);              // also: everyone is done with the other buffer
+            if (more && threadIdx.x == 0) {
+                const int cnt = min(kScanTile, n - (t + 1) * kScanTile);
+                mbar_expect_tx(&pp.bars[buf ^ 1], cnt * 16u);
+                bulk_g2s(pp.tiles + (buf ^ 1) * kScanTile, sc.sph_filter + (size_t)(t + 1) * kScanTile, cnt * 16u,
+                         &pp.bars[buf ^ 1]);
+            }
+        }
+        mbar_wait(&pp.bars[buf], (pp.phase_bits >> buf) & 1u);
+        pp.phase_bits ^= 1u << buf;
+        if (active) body(pp.tiles + buf * kScanTile, min(kScanTile, n - t * kScanTile), t * kScanTile);
+        if (!more) break;
+    }
+    __syncthreads();                                      // the buffers are free for the next batch
+}
+
+// The filter over one tile for one ray.  Groups of kScanGroup spheres are tested branch-free (the
+// pass bits collect in a mask, so the loads and FMAs of a group overlap); survivors — a few per
+// thousand — then go through stage 2 and the literal FP64 test.
+constexpr int kScanGroup = 8;
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, const RaySlot &ray, const float4 *tile,
+                                          int cnt, int base, int skip_obj, int seed_obj, Hit &best, float &cullk,
+                                          bool &active, Tally<COUNT> &tl)
+{
+    const float nbcull = -f.bcull, ntheta = -f.theta;
+#pragma unroll 1
+    for (int k0 = 0; k0 < cnt; k0 += kScanGroup) {
+        unsigned int mask = 0;
+#pragma unroll
+        for (int u = 0; u < kScanGroup; u++) {
+            const float4 fs = tile[k0 + u];              // past `cnt` the buffer holds stale spheres: masked below
+            const float cx = fs.x - f.ox, cy = fs.y - f.oy, cz = fs.z - f.oz;
+            const float b = __fmaf_rn(f.dz, cz, __fmaf_rn(f.dy, cy, f.dx * cx));
+            const float w = __fmaf_rn(cx, cx, __fmaf_rn(cy, cy, __fmaf_rn(cz, cz, -fs.w)));
+            const float v = __fmaf_rn(b, b, -w);
+            // stage 1 (!(v < -theta)) and the "entirely behind the origin" cull of stage 2
+            if (!(v < ntheta) && !(b < nbcull)) mask |= 1u << u;
+        }
+        if (k0 + kScanGroup > cnt) mask &= (1u << (cnt - k0)) - 1u;
+        while (mask) {
+            const int u = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int k = k0 + u;
+            const float4 fs = tile[k];
+            float b, v;
+            filter_stage1(f, fs, b, v);
+            if (!filter_stage2(f, fs, b, v, cullk)) continue;
+            const int sph = base + k;
+            const int code = obj_code(OBJ_SPHERE, sph);
+            if (code == skip_obj) continue;
+            double t;
+            TALLY(exact_sph);
+            if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+                const int ord = sc.sph_order[sph];
+                if (better(t, ord, best)) {
+                    best.t = t; best.order = ord; best.obj = code;
+                    cullk = cullk_from(f, ray.inv_sqrt_a(), best);
+                    if constexpr (ANY) {                  // a shadow ray only asks whether one exists
+                        if constexpr (COUNT) tl.filter += min(k0 + kScanGroup, cnt);
+                        active = false;
+                        return;
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (COUNT) tl.filter += cnt;
+    (void)seed_obj;
+}
+
+template <bool FIRST, bool COUNT>
+__global__ void __launch_bounds__(kWfThreads, ERT_SCAN_MINBLOCKS)
+wf_scan_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
+             const __grid_constant__ WfBuf wf, int bounce)
+{
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ unsigned long long s_base;
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    ScanPipe pp;
+    pp.tiles = reinterpret_cast<float4 *>(scan_smem);
+    pp.bars = bars;
+    pp.phase_bits = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned long long n = FIRST ? (unsigned long long)wf.n_pad
+                                       : (unsigned long long)wf.ctr[(bounce - 1) * kWfCtr + WF_NNEXT];
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_PATH);
+    Tally<COUNT> tl;
+    unsigned int rays = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kWfThreads);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        if (base >= n) break;
+        const unsigned long long i64 = base + threadIdx.x;
+        bool valid = i64 < n;
+        const unsigned int i = (unsigned int)i64;
+        Hit best;
+        best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+        SRay f;
+        float cullk = 0.f;
+        bool active = false;
+        if (valid) {
+            int pid;
+            d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
+            path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
+            if (valid) {
+                rays++;
+                scan_others<COUNT>(sc, O, D, best, -1, tl);
+                double a, inv;
+                make_sray(sc, O, D, f, a, inv);
+                ray.put(O, D, a, inv);
+                cullk = cullk_from(f, inv, best);
+                active = sc.n_spheres > 0;
+            }
+        }
+        scan_all_tiles(sc, pp, active, [&](const float4 *tile, int cnt, int tbase) {
+            scan_tile<false, COUNT>(sc, f, ray, tile, cnt, tbase, -1, -1, best, cullk, active, tl);
+        });
+        if (i64 < n) {
+            __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
+            __stcs(wf.res_t + i, best.t);
+        }
+    }
+    flush_counters<COUNT>(fp, (int)rays, tl);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWfThreads, ERT_SCAN_MINBLOCKS)
+wf_scan_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
+               const __grid_constant__ WfBuf wf, int bounce)
+{
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ unsigned long long s_base;
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    ScanPipe pp;
+    pp.tiles = reinterpret_cast<float4 *>(scan_smem);
+    pp.bars = bars;
+    pp.phase_bits = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned int n_hits = ctr[WF_NHITS];
+    const unsigned long long total = (unsigned long long)n_hits * (unsigned long long)sc.n_lights;
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_SHADOW);
+    const size_t np = (size_t)wf.n_pad;
+    Tally<COUNT> tl;
+    unsigned int rays = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kWfThreads);
+        __syncthreads();
+        const unsigned long long base = s_base;
+        if (base >= total) break;
+        const unsigned long long j = base + threadIdx.x;
+        const bool valid = j < total;
+        unsigned int l = 0, h = 0;
+        Hit best;
+        best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+        SRay f;
+        float cullk = 0.f;
+        bool active = false, lit = false;
+        int target = -1;
+        if (valid) {
+            l = (unsigned int)(j / n_hits);
+            h = (unsigned int)(j - (unsigned long long)l * n_hits);
+            rays++;
+            const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+            d3 P = mk(r0.x, r0.y, r0.z);
+            target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
+            const int order = (int)(__double_as_longlong(r0.w) >> 32);
+            const double *lt = sc.lights + 9 * (size_t)l;
+            d3 O = mk(lt[3], lt[4], lt[5]);
+            d3 D = vnormalize(vsub(P, O));                         // erl:257-260
+            double a = D.x * D.x + D.y * D.y + D.z * D.z;
+            double t;
+            if (object_exact(sc, target, O, D, a, t)) {              // erl:263 needs the target hit
+                best.t = t; best.order = order; best.obj = target;
+                scan_others<COUNT>(sc, O, D, best, target, tl);
+                lit = best.obj == target;
+                if (lit && sc.n_spheres > 0) {
+                    double a2, inv;
+                    make_sray(sc, O, D, f, a2, inv);
+                    ray.put(O, D, a2, inv);
+                    cullk = cullk_from(f, inv, best);
+                    active = true;
+                }
+            }
+        }
+        scan_all_tiles(sc, pp, active, [&](const float4 *tile, int cnt, int tbase) {
+            scan_tile<true, COUNT>(sc, f, ray, tile, cnt, tbase, target, target, best, cullk, active, tl);
+        });
+        if (valid) wf.lit[(size_t)l * np + h] = lit && best.obj == target;
+    }
+    flush_counters<COUNT>(fp, (int)rays, tl);
+}
+
 // Folds the lights of every hit of one bounce (erl:209-252 in forward form, see pix_consume)
 // and emits the reflection rays of the next bounce.
 __global__ void __launch_bounds__(kWfThreads)

@@ -219,6 +219,8 @@ ERT_API int ert_host_unregister(void *p);
 /* Measured FP32 issue peak of `device`: lane-instructions per second of a
  * register-resident FFMA loop (the roofline denominator of the scan kernels). */
 ERT_API int ert_fp32_peak(int device, double *lane_instr_per_s);
+/* The same loop with three register operands per FFMA, the form the intersection kernels issue. */
+ERT_API int ert_fp32_peak_rrr(int device, double *lane_instr_per_s);
 
 /* Writes a buffer larger than L2 on `device` (bench hygiene between timed steps). */
 ERT_API int ert_l2_flush(int device);
