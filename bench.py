@@ -274,9 +274,10 @@ def gpu_arm(args, rank, world, local_rank):
 
     # warm-up through the full end-to-end path
     for i in range(max(args.warmup, 0)):
-        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), host_ptr=host_ptr,
+        k = i % n_host                               # the pipelined loop uses two slots: warm both
+        dev.render_async(w, h, depth, slot=k, camera=camera_for(i), host_ptr=hosts[k].ptr,
                          host_bytes=frame_bytes, **common)
-        dev.wait(0)
+        dev.wait(k)
 
     # instrumented (untimed) run: test counters for the roofline accounting
     dev.render_async(w, h, depth, slot=0, flags=_lib.FLAG_COUNT_TESTS, camera=camera_for(0), **common)
