@@ -214,9 +214,9 @@ def gpu_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device is visible; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's version banner goes to stdout; the bench prints exactly one line there
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner (levels VERSION and WARN) to stdout; the bench prints exactly one
+        # line there, so NCCL's log goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
