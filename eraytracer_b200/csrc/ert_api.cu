@@ -370,9 +370,9 @@ int upload_scene(ert_scene *s)
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, s->device));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true>, kWfThreads, 0));
         s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false, true>, kWfThreads, 0));
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false, true>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
@@ -603,14 +603,19 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         const bool sort = b >= 1 && !no_sort && !scan;
         if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
         else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
-        else if (b == 0) wf_trace_path<true, COUNT><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b == 0) wf_trace_path<true, COUNT, true><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b < ERT_WF_REFILL_FROM && sort) wf_trace_path<false, COUNT, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT, true><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         else wf_trace_path_refill<COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        // the batch kernels emit their hit records themselves unless the hits are to be binned
+        const bool emitted = !scan && (b == 0 || (b < ERT_WF_REFILL_FROM && !sort));
         n++;
         TICK(0);
         WF_CHECK("wf_trace_path");
         if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
-        if (b == 0) {
+        if (emitted) {
+            n--;                                 // no separate launch
+        } else if (b == 0) {
             wf_emit_hits<true, false><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
         } else if (!sort) {
             wf_emit_hits<false, false><<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);

@@ -505,6 +505,22 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
 // lanes below `lane` in mask m
 __device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc(m & ((1u << lane) - 1u)); }
 
+__device__ __forceinline__ void write_hit(HitHead *heads, HitTail *tails, size_t s, d3 P, d3 N, d3 D, int obj, int order,
+                                          int pid)
+{
+    HitHead hh;
+    HitTail ht;
+    hh.P[0] = P.x; hh.P[1] = P.y; hh.P[2] = P.z; hh.obj = obj; hh.order = order;
+    ht.N[0] = N.x; ht.N[1] = N.y; ht.N[2] = N.z; ht.pid = pid; ht.pad0 = 0;
+    ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.pad1 = 0.0;
+    const uint4 *sh = reinterpret_cast<const uint4 *>(&hh);
+    const uint4 *st = reinterpret_cast<const uint4 *>(&ht);
+    uint4 *dh = reinterpret_cast<uint4 *>(heads + s);
+    uint4 *dt = reinterpret_cast<uint4 *>(tails + s);
+    dh[0] = sh[0]; dh[1] = sh[1];
+    dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+}
+
 // Work distribution of the traversal kernels.  A warp owns a chunk of kWfChunk consecutive
 // queue entries at a time (one atomic per chunk) and works through it in batches of 32, so the
 // rays a lane sees one after another are 32 entries apart in the (binned) queue: neighbours in
@@ -543,8 +559,11 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 }
 
 // Path rays of one bounce: nearest_object_intersecting_ray/2 (erl:300-346) for every ray of
-// the path queue (FIRST: for every pixel, rays generated on the fly).
-template <bool FIRST, bool COUNT>
+// the path queue (FIRST: for every pixel, rays generated on the fly).  EMIT: the batch also turns
+// its hits into hit records (what wf_emit_hits does from the result arrays) — the warp is back
+// together after every batch, so the FP64 of the hit location and normal runs on full warps and
+// the results never travel through HBM.
+template <bool FIRST, bool COUNT, bool EMIT>
 __global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
 wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
               const __grid_constant__ WfBuf wf, int bounce)
@@ -564,23 +583,23 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
     while (next_chunk(cursor, n, lane, begin, end)) {
         for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
             const unsigned long long i64 = b0 + lane;
-            if (i64 >= end) continue;
+            const bool in_range = i64 < end;
             const unsigned int i = (unsigned int)i64;
-            bool valid;
-            int pid;
+            bool valid = false;
+            int pid = 0;
             Hit best;
             best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
-            {
+            if (in_range) {
                 d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
                 path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
                 if (valid) {
                     rays++;
                     scan_others<COUNT>(sc, O, D, best, -1, tl);
+                    SRay f;
+                    double a, inv;
+                    make_sray(sc, O, D, f, a, inv);
+                    ray.put(O, D, a, inv);
                     if (sc.n_spheres > 0) {
-                        SRay f;
-                        double a, inv;
-                        make_sray(sc, O, D, f, a, inv);
-                        ray.put(O, D, a, inv);
                         int skip = -1;
                         if (hint >= 0) {
                             // seed the search with the previous ray's sphere: a real candidate of the
@@ -602,8 +621,26 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     }
                 }
             }
-            __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
-            __stcs(wf.res_t + i, best.t);
+            if constexpr (!EMIT) {
+                if (in_range) {
+                    __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
+                    __stcs(wf.res_t + i, best.t);
+                }
+            } else {
+                const bool hit = valid && best.obj >= 0;
+                const unsigned int m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    unsigned int slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)__popc(m));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                    if (hit) {
+                        const d3 O = ray.O(), D = ray.D();
+                        const d3 P = vadd(O, vscale(D, best.t));      // erl:384-387 / 443-447 / 471-475
+                        const d3 N = hit_normal(sc, best.obj, P);
+                        write_hit(wf.hit_head, wf.hit_tail, slot0 + rank_in(m, lane), P, N, D, best.obj, best.order, pid);
+                    }
+                }
+            }
         }
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
@@ -730,19 +767,7 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
             d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
             d3 N = hit_normal(sc, r.x, P);
             size_t s = slot0 + rank_in(m, lane);
-            HitHead hh;
-            HitTail ht;
-            hh.P[0] = P.x; hh.P[1] = P.y; hh.P[2] = P.z; hh.obj = r.x; hh.order = r.y;
-            ht.N[0] = N.x; ht.N[1] = N.y; ht.N[2] = N.z; ht.pid = pid; ht.pad0 = 0;
-            ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.pad1 = 0.0;
-            {
-                const uint4 *sh = reinterpret_cast<const uint4 *>(&hh);
-                const uint4 *st = reinterpret_cast<const uint4 *>(&ht);
-                uint4 *dh = reinterpret_cast<uint4 *>(out_head + s);
-                uint4 *dt = reinterpret_cast<uint4 *>(out_tail + s);
-                dh[0] = sh[0]; dh[1] = sh[1];
-                dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
-            }
+            write_hit(out_head, out_tail, s, P, N, D, r.x, r.y, pid);
             if constexpr (SORT) {
                 unsigned int key = sort_cell(sc, P);
                 wf.r_key[s] = key;
