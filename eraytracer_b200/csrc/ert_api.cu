@@ -378,6 +378,24 @@ int upload_scene(ert_scene *s)
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
         s->wf_grid[3] = prop.multiProcessorCount * std::max(nb, 1);
+        // The walks live on L1 (tree nodes + the local-memory stacks).  Ask for exactly the shared memory
+        // the resident blocks need, so that the rest of the 256 KB array serves as L1 (measured on C4:
+        // 23.5 -> 23.1 ms against the driver's default split; too small a carve-out halves the occupancy).
+        auto carve = [&](const void *fn, int blocks_per_sm) -> int {
+            cudaFuncAttributes fa;
+            CU(cudaFuncGetAttributes(&fa, fn));
+            size_t need = (size_t)blocks_per_sm * (fa.sharedSizeBytes + 1024);      // 1 KB per block is reserved
+            int pct = (int)((need * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor) + 1;
+            if (const char *e = getenv("ERT_WF_CARVEOUT")) pct = atoi(e);
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100)));
+            return ERT_OK;
+        };
+        if ((rc = carve((const void *)wf_trace_path<true, false, true>, s->wf_grid[0] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, true>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path_refill<false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_shadow<false, true>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_shadow<false, false>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         CU(cudaFuncSetAttribute(wf_scan_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
         CU(cudaFuncSetAttribute(wf_scan_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
         CU(cudaFuncSetAttribute(wf_scan_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
