@@ -104,18 +104,27 @@ struct SRay {
 struct RaySlot {
     double *p;                                           // &slots[0][threadIdx.x], stride kWfThreads
     __device__ __forceinline__ double get(int k) const { return p[k * kWfThreads]; }
-    __device__ __forceinline__ void put(d3 O, d3 D, double a, double inv)
+    __device__ __forceinline__ void put(d3 O, d3 D, double, double)
     {
         p[0] = O.x; p[kWfThreads] = O.y; p[2 * kWfThreads] = O.z;
         p[3 * kWfThreads] = D.x; p[4 * kWfThreads] = D.y; p[5 * kWfThreads] = D.z;
-        p[6 * kWfThreads] = a; p[7 * kWfThreads] = inv;
     }
     __device__ __forceinline__ d3 O() const { return mk(get(0), get(1), get(2)); }
     __device__ __forceinline__ d3 D() const { return mk(get(3), get(4), get(5)); }
-    __device__ __forceinline__ double a() const { return get(6); }
-    __device__ __forceinline__ double inv_sqrt_a() const { return get(7); }
+    // a = D.D and 1/sqrt(a) are recomputed where the rare literal tests need them (same expressions
+    // as make_sray), which keeps the slot at 48 bytes per thread: shared memory here is L1 lost
+    __device__ __forceinline__ double a() const
+    {
+        const d3 d = D();
+        return d.x * d.x + d.y * d.y + d.z * d.z;
+    }
+    __device__ __forceinline__ double inv_sqrt_a() const
+    {
+        const double aa = a();
+        return (fabs(aa - 1.0) <= 1e-9) ? (1.5 - 0.5 * aa) : 1.0 / sqrt(aa);
+    }
 };
-constexpr int kRaySlotDoubles = 8;
+constexpr int kRaySlotDoubles = 6;
 #define ERT_KAPPA 1.00006103515625f   /* 1 + 2^-14 >= (1+2^-16)/(1-2^-16): slab slack as one factor */
 
 __device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &f, double &a_out, double &inv_out)
