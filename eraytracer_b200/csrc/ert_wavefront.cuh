@@ -217,13 +217,14 @@ template <bool ANY>
 struct Trav {
     int node, sp;
     float cullk;
-    int stack[kBvhStack];
 };
+// The stack is a separate local array (passed as `stack`): as a member it would drag node, sp and
+// cullk into local memory with it wherever the state outlives a loop iteration.
 
 template <bool ANY>
-__device__ __forceinline__ void trav_start(Trav<ANY> &tr, const SRay &f, double inv_sqrt_a, const Hit &best)
+__device__ __forceinline__ void trav_start(Trav<ANY> &tr, int *stack, const SRay &f, double inv_sqrt_a, const Hit &best)
 {
-    tr.stack[0] = kTravDone;
+    stack[0] = kTravDone;
     tr.sp = 1;
     tr.node = 0;
     tr.cullk = cullk_from(f, inv_sqrt_a, best);
@@ -235,16 +236,16 @@ __device__ __forceinline__ void trav_start(Trav<ANY> &tr, const SRay &f, double 
 // 6 % of box tests it saved.  (A triangle incumbent can have t < 0, erl:402-455 has no t >= 0 test:
 // then cullk is negative and every box test fails, which is right — no sphere has t < 0.)
 template <bool ANY>
-__device__ __forceinline__ void trav_pop(Trav<ANY> &tr)
+__device__ __forceinline__ void trav_pop(Trav<ANY> &tr, const int *stack)
 {
     --tr.sp;
     WF_ASSERT(tr.sp >= 0, "sp %d", tr.sp);
-    tr.node = tr.stack[tr.sp];
+    tr.node = stack[tr.sp];
 }
 
 // returns true when the search is over
 template <bool ANY, bool COUNT>
-__device__ __forceinline__ bool trav_step(Trav<ANY> &tr, const DevScene &sc, const RaySlot &ray, const SRay &f,
+__device__ __forceinline__ bool trav_step(Trav<ANY> &tr, int *stack, const DevScene &sc, const RaySlot &ray, const SRay &f,
                                           Hit &best, int skip_obj, int seed_obj, Tally<COUNT> &tl)
 {
     while (tr.node >= 0) {
@@ -272,7 +273,7 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, const DevScene &sc, con
             bool swap = tn1 < tn0;
             tr.node = swap ? ch.y : ch.x;
             if (tr.sp < kBvhStack) {
-                tr.stack[tr.sp] = swap ? ch.x : ch.y;
+                stack[tr.sp] = swap ? ch.x : ch.y;
                 tr.sp++;
             }
         } else if (h0) {
@@ -280,7 +281,7 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, const DevScene &sc, con
         } else if (h1) {
             tr.node = ch.y;
         } else {
-            trav_pop(tr);
+            trav_pop(tr, stack);
         }
     }
     if (tr.node == kTravDone) return true;
@@ -297,7 +298,7 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, const DevScene &sc, con
     if constexpr (ANY) {
         if (best.obj != seed_obj) return true;
     }
-    trav_pop(tr);
+    trav_pop(tr, stack);
     return tr.node == kTravDone;
 }
 
@@ -310,11 +311,12 @@ __device__ void trace_ray_wavefront(const DevScene &sc, d3 O, d3 D, Hit &best)
     SRay f;
     Tally<false> tl;
     Trav<false> tr;
+    int stack[kBvhStack];
     double a, inv;
     make_sray(sc, O, D, f, a, inv);
     ray.put(O, D, a, inv);
-    trav_start(tr, f, inv, best);
-    while (!trav_step<false, false>(tr, sc, ray, f, best, -1, -1, tl)) { }
+    trav_start(tr, stack, f, inv, best);
+    while (!trav_step<false, false>(tr, stack, sc, ray, f, best, -1, -1, tl)) { }
 }
 
 // ------------------------------------------------------------------ pixel <-> queue index
@@ -624,8 +626,9 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                             }
                         }
                         Trav<false> tr;
-                        trav_start(tr, f, inv, best);
-                        while (!trav_step<false, COUNT>(tr, sc, ray, f, best, skip, -1, tl)) { }
+                        int stack[kBvhStack];
+                        trav_start(tr, stack, f, inv, best);
+                        while (!trav_step<false, COUNT>(tr, stack, sc, ray, f, best, skip, -1, tl)) { }
                         if (best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
                     }
                 }
@@ -690,6 +693,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
     Hit best;
     best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
     Trav<false> tr;
+    int stack[kBvhStack];
     tr.node = kTravDone; tr.sp = 0; tr.cullk = 0.f;
     for (;;) {
         const unsigned int idle = __ballot_sync(0xffffffffu, !have);
@@ -715,7 +719,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                         double a, inv;
                         make_sray(sc, O, D, f, a, inv);
                         ray.put(O, D, a, inv);
-                        trav_start(tr, f, inv, best);
+                        trav_start(tr, stack, f, inv, best);
                         have = true;
                     } else {
                         wf.res_hit[i] = make_int2(best.obj, best.order);
@@ -730,7 +734,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
         }
         for (;;) {
             if (have) {
-                if (trav_step<false, COUNT>(tr, sc, ray, f, best, -1, -1, tl)) {
+                if (trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl)) {
                     __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
                     __stcs(wf.res_t + idx, best.t);
                     have = false;
@@ -888,8 +892,9 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                         if (lit) {
                             ray.put(O, D, a2, inv);
                             Trav<true> tr;
-                            trav_start(tr, f, inv, best);
-                            while (!trav_step<true, COUNT>(tr, sc, ray, f, best, target, target, tl)) { }
+                            int stack[kBvhStack];
+                            trav_start(tr, stack, f, inv, best);
+                            while (!trav_step<true, COUNT>(tr, stack, sc, ray, f, best, target, target, tl)) { }
                             lit = best.obj == target;
                             if (!lit && obj_type(best.obj) == OBJ_SPHERE) { hint = obj_index(best.obj); found = hint; }
                         }
