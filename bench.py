@@ -364,11 +364,13 @@ def gpu_arm(args, rank, world, local_rank):
         # roofline (rank 0's launches).  Wavefront frames: the dominant kernel class is the BVH walk of
         # the path rays (wf_trace_path / wf_trace_path_refill); other accels are one kernel per frame.
         k_s = (kernel_ms / steps) * 1e-3
-        frame_lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10
+        # cell steps of the grid walks belong to the path class (shadow rays never use the cell grid)
+        cell_instr = counted.get("cell_steps", 0) * 4
+        frame_lane_instr = counted["box_tests"] * 6 + counted["sphere_filter_tests"] * 10 + cell_instr
         wavefront = split["path_launches"] > 0
         dom = "path" if split["path_ms"] >= split["shadow_ms"] else "shadow"
         if wavefront:
-            lane_instr = counted[dom + "_box_tests"] * 6 + counted[dom + "_filter_tests"] * 10
+            lane_instr = counted[dom + "_box_tests"] * 6 + counted[dom + "_filter_tests"] * 10 + (cell_instr if dom == "path" else 0)
             dom_s = (split[dom + "_ms"] / steps) * 1e-3
         else:
             lane_instr, dom_s = frame_lane_instr, k_s
@@ -412,13 +414,15 @@ def gpu_arm(args, rank, world, local_rank):
                 "frac": achieved / peak, "traffic": traffic,
                 "kernel": ({("bvh", "path"): "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
                             ("bvh", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
+                            ("grid", "path"): "wf_trace_path<GRID> + wf_trace_path_refill<GRID> (cell-grid walks of the path rays, all bounces)",
+                            ("grid", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
                             ("linear", "path"): "wf_scan_path (brute-force filter scan of the path rays)",
                             ("linear", "shadow"): "wf_scan_shadow (brute-force filter scan of the shadow rays)"}
                            .get((counted["accel_used"], dom), "?") if wavefront else
                            {"bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
                             "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?")),
-                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test of the "
-                              "named kernels (counts from an instrumented run of the same frame on rank 0), divided "
+                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test + 4 per "
+                              "cell step (FFMA, FADD, two FMNMX) of the named kernels (counts from an instrumented run of the same frame on rank 0), divided "
                               "by their CUDA-event time inside the timed steps",
                 "launches_per_step": (split[dom + "_launches"] / steps) if wavefront else 1,
                 "avg_launch_ms": (split[dom + "_ms"] / max(split[dom + "_launches"], 1)) if wavefront else kernel_ms / steps,
@@ -426,10 +430,12 @@ def gpu_arm(args, rank, world, local_rank):
                 "box_tests": int(counted[dom + "_box_tests"] if wavefront else counted["box_tests"]),
                 "sphere_filter_tests": int(counted[dom + "_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
                 "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
+                "cell_steps": int(counted.get("cell_steps", 0)),
                 "frame": {"lane_instr": int(frame_lane_instr), "frac": frame_lane_instr / k_s / peak,
                           "box_tests": int(counted["box_tests"]),
                           "sphere_filter_tests": int(counted["sphere_filter_tests"]),
-                          "class_frac": {c: ((counted[c + "_box_tests"] * 6 + counted[c + "_filter_tests"] * 10)
+                          "class_frac": {c: ((counted[c + "_box_tests"] * 6 + counted[c + "_filter_tests"] * 10
+                                              + (cell_instr if c == "path" else 0))
                                              / max(split[c + "_ms"] / steps * 1e-3, 1e-12) / peak)
                                          for c in ("path", "shadow")} if wavefront else None,
                           "ms": {"path": split["path_ms"] / steps, "shadow": split["shadow_ms"] / steps,
@@ -470,7 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh", "bvh_mega"))
+    ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh", "bvh_mega", "grid"))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sample at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -235,7 +235,7 @@ static ERL_NIF_TERM nif_scene_upload(ErlNifEnv *env, int argc, const ERL_NIF_TER
     return enif_make_tuple2(env, enif_make_atom(env, "ok"), term);
 }
 
-/* Opts: proplist of {format, rgb8|f32|f64} | {accel, auto|exact|linear|bvh|bvh_mega} |
+/* Opts: proplist of {format, rgb8|f32|f64} | {accel, auto|exact|linear|bvh|bvh_mega|grid} |
  *       {part, {BandRows, NParts, Part}} | {camera, CameraRecord} */
 static int decode_opts(ErlNifEnv *env, ERL_NIF_TERM opts, ert_render_params *p, ert_camera *cam)
 {
@@ -255,6 +255,7 @@ static int decode_opts(ErlNifEnv *env, ERL_NIF_TERM opts, ert_render_params *p, 
             else if (is_atom_named(env, e[1], "linear")) p->accel = ERT_ACCEL_LINEAR;
             else if (is_atom_named(env, e[1], "bvh")) p->accel = ERT_ACCEL_BVH;
             else if (is_atom_named(env, e[1], "bvh_mega")) p->accel = ERT_ACCEL_BVH_MEGAKERNEL;
+            else if (is_atom_named(env, e[1], "grid")) p->accel = ERT_ACCEL_GRID;
             else return 0;
         } else if (is_atom_named(env, e[0], "part")) {
             int a3;

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ERT_B200_LIB") or os.path.join(HERE, "lib", "libert_b
 
 ERT_OK, ERT_ERR_BADARG, ERT_ERR_NO_DEVICE, ERT_ERR_CUDA, ERT_ERR_NOMEM = 0, 1, 2, 3, 4
 FMT_RGB8, FMT_F32, FMT_F64 = 0, 1, 2
-ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL = 0, 1, 2, 3, 4
+ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL, ACCEL_GRID = 0, 1, 2, 3, 4, 5
 FLAG_COUNT_TESTS = 1
 FLAG_WF_UNSORTED = 2
 FLAG_NO_LIGHT_GRID = 4
@@ -24,7 +24,7 @@ MAX_SLOTS = 4
 FORMATS = {"rgb8": FMT_RGB8, "f32": FMT_F32, "f64": FMT_F64}
 FORMAT_DTYPES = {FMT_RGB8: np.uint8, FMT_F32: np.float32, FMT_F64: np.float64}
 ACCELS = {"auto": ACCEL_AUTO, "exact": ACCEL_EXACT, "linear": ACCEL_LINEAR, "bvh": ACCEL_BVH,
-          "bvh_mega": ACCEL_BVH_MEGAKERNEL}
+          "bvh_mega": ACCEL_BVH_MEGAKERNEL, "grid": ACCEL_GRID}
 ACCEL_NAMES = {v: k for k, v in ACCELS.items()}
 
 
@@ -70,10 +70,11 @@ class Stats(ctypes.Structure):
                 ("path_box_tests", ctypes.c_uint64), ("path_filter_tests", ctypes.c_uint64),
                 ("shadow_box_tests", ctypes.c_uint64), ("shadow_filter_tests", ctypes.c_uint64),
                 ("path_ms", ctypes.c_double), ("shadow_ms", ctypes.c_double), ("other_ms", ctypes.c_double),
-                ("path_launches", ctypes.c_uint64), ("shadow_launches", ctypes.c_uint64)]
+                ("path_launches", ctypes.c_uint64), ("shadow_launches", ctypes.c_uint64),
+                ("cell_steps", ctypes.c_uint64), ("has_cell_grid", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
 
 
 # numpy views of the element records (same layout as the C structs)

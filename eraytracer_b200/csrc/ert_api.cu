@@ -16,6 +16,7 @@
 
 #include "bvh_build.h"
 #include "light_grid.h"
+#include "cell_grid.h"
 #include "ert_device.cuh"
 #include "ert_wavefront.cuh"
 
@@ -66,6 +67,7 @@ struct HostScene {
     std::vector<float> leaf_filter;    // [n][4]
     Bvh bvh;
     std::vector<LightGrid> lgrids;     // direction grids of the first lights (shadow queries)
+    CellGrid cgrid;                    // uniform cell grid over the spheres (path rays)
     float r_max = 0, pad_c_max = 0, eta_c_max = 0, abs_max = 0;
     float grid_lo[3] = {0, 0, 0}, grid_scale[3] = {0, 0, 0};
     int n_lights = 0, n_planes = 0, n_tris = 0, n_spheres = 0;
@@ -99,7 +101,7 @@ struct Slot {
 
 struct ert_scene {
     int device = 0;
-    int wf_grid[4] = {0, 0, 0, 0};     // persistent grid sizes: path(first), path, shadow, shade
+    int wf_grid[6] = {0, 0, 0, 0, 0, 0};   // persistent grid sizes: path(first), path, shadow, shade, cell-grid path(first), path
     int wf_grid_scan = 0;              // brute-force scan kernels (2 blocks per SM)
     HostScene host;
     DevScene dev{};
@@ -280,6 +282,14 @@ int flatten(const ert_scene_desc *d, HostScene &h)
             build_light_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, &h.lights[(size_t)g * 9 + 3],
                              res, h.lgrids[(size_t)g]);
     }
+    {
+        // cell grid for the path rays; ERT_CELL_GRID=0 turns it off, ERT_CELL_GRID_DENSITY = cells per sphere
+        double density = kCellGridDensity;
+        if (const char *e = getenv("ERT_CELL_GRID_DENSITY")) density = atof(e);
+        const char *off = getenv("ERT_CELL_GRID");
+        if (!(off && atoi(off) == 0))
+            build_cell_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, h.abs_max, density, h.cgrid);
+    }
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
@@ -349,6 +359,19 @@ int upload_scene(ert_scene *s)
         d.lgrids = lgd;
         d.lg_count = (int)lg.size();
     }
+    {
+        const CellGrid &G = h.cgrid;
+        const unsigned int *cells; const float *rf; const int *rs; const int *big;
+        if ((rc = upload<unsigned int>(s, G.cells, &cells)) != ERT_OK) return rc;
+        if ((rc = upload<float>(s, G.ref_filter, &rf)) != ERT_OK) return rc;
+        if ((rc = upload<int>(s, G.ref_sph, &rs)) != ERT_OK) return rc;
+        if ((rc = upload<int>(s, G.big, &big)) != ERT_OK) return rc;
+        d.cg.cells = cells; d.cg.ref_filter = reinterpret_cast<const float4 *>(rf); d.cg.ref_sph = rs; d.cg.big = big;
+        d.cg.n_big = (int)G.big.size(); d.cg.enabled = G.enabled ? 1 : 0;
+        d.cg.rx = G.res[0]; d.cg.ry = G.res[1]; d.cg.rz = G.res[2];
+        for (int a = 0; a < 3; a++) { d.cg.lo[a] = G.lo[a]; d.cg.hi[a] = G.hi[a]; }
+        d.cg.cs = G.cs; d.cg.eps = G.eps;
+    }
     d.n_nodes = (int)h.bvh.nodes.size();
     for (int a = 0; a < 3; a++) { d.grid_lo[a] = h.grid_lo[a]; d.grid_scale[a] = h.grid_scale[a]; }
     d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
@@ -370,10 +393,14 @@ int upload_scene(ert_scene *s)
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, s->device));
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true, false>, kWfThreads, 0));
         s->wf_grid[0] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false, true>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<false, false, true, false>, kWfThreads, 0));
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true, true>, kWfThreads, 0));
+        s->wf_grid[4] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path_refill<false, true>, kWfThreads, 0));
+        s->wf_grid[5] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false, true>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
@@ -390,10 +417,14 @@ int upload_scene(ert_scene *s)
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100)));
             return ERT_OK;
         };
-        if ((rc = carve((const void *)wf_trace_path<true, false, true>, s->wf_grid[0] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        if ((rc = carve((const void *)wf_trace_path<false, false, true>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        if ((rc = carve((const void *)wf_trace_path<false, false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        if ((rc = carve((const void *)wf_trace_path_refill<false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<true, false, true, false>, s->wf_grid[0] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, true, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path_refill<false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<true, false, true, true>, s->wf_grid[4] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, true, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path<false, false, false, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path_refill<false, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, true>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, false>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         CU(cudaFuncSetAttribute(wf_scan_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
@@ -449,7 +480,7 @@ int check_params(const ert_render_params *p)
     if (p->width <= 0 || p->height <= 0) return fail(ERT_ERR_BADARG, "width and height must be > 0 (erl:89)");
     if (p->depth < 0) return fail(ERT_ERR_BADARG, "recursion depth must be >= 0");
     if (p->format < ERT_FMT_RGB8 || p->format > ERT_FMT_F64) return fail(ERT_ERR_BADARG, "unknown output format");
-    if (p->accel < ERT_ACCEL_AUTO || p->accel > ERT_ACCEL_BVH_MEGAKERNEL) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (p->accel < ERT_ACCEL_AUTO || p->accel > ERT_ACCEL_GRID) return fail(ERT_ERR_BADARG, "unknown accel");
     if (p->n_parts > 1 && p->band_rows > 0 && (p->part < 0 || p->part >= p->n_parts))
         return fail(ERT_ERR_BADARG, "part must be in [0, n_parts)");
     if (p->band_rows < 0) return fail(ERT_ERR_BADARG, "band_rows must be >= 0");
@@ -458,10 +489,11 @@ int check_params(const ert_render_params *p)
 
 int pick_accel(const ert_scene *s, int requested)
 {
+    if (requested == ERT_ACCEL_GRID) return s->host.cgrid.enabled ? ERT_ACCEL_GRID : ERT_ACCEL_BVH;
     if (requested != ERT_ACCEL_AUTO) return requested;
     if (s->host.n_spheres <= 16) return ERT_ACCEL_EXACT;
     if (s->host.n_spheres <= 192) return ERT_ACCEL_LINEAR;
-    return ERT_ACCEL_BVH;
+    return s->host.cgrid.enabled ? ERT_ACCEL_GRID : ERT_ACCEL_BVH;
 }
 
 // device -> host placement of the part's rows inside the full frame
@@ -564,7 +596,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
 
 template <bool COUNT>
 int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unsorted, bool no_grid, bool timed,
-                     bool scan, uint64_t *launches)
+                     bool scan, bool cells, uint64_t *launches)
 {
     WfBuf wf{};
     int rc;
@@ -597,6 +629,9 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     // Binning hits by location pays when shadow rays walk the BVH (coherent warps); with a direction
     // grid for every light it costs more than the path rays gain from it (measured on C4: 29.2 vs 27.8 ms).
     static const bool force_sort = getenv("ERT_WF_SORT") != nullptr;
+    // experiments: first bounce whose path rays use the cell grid / the refilling form of that kernel
+    static const int cells_from = getenv("ERT_CELLS_FROM") ? atoi(getenv("ERT_CELLS_FROM")) : 0;
+    static const int cells_refill_from = getenv("ERT_CELLS_REFILL_FROM") ? atoi(getenv("ERT_CELLS_REFILL_FROM")) : ERT_WF_REFILL_FROM;
     const bool shadows_walk = !no_grid ? d.lg_count < d.n_lights : true;
     const bool no_sort = unsorted || (!shadows_walk && !force_sort) || getenv("ERT_WF_NO_SORT") != nullptr;
 #define WF_CHECK(what)                                                                 \
@@ -621,12 +656,20 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         const bool sort = b >= 1 && !no_sort && !scan;
         if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
         else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
-        else if (b == 0) wf_trace_path<true, COUNT, true><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else if (b < ERT_WF_REFILL_FROM && sort) wf_trace_path<false, COUNT, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT, true><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else wf_trace_path_refill<COUNT><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (cells && b >= cells_from) {
+            // path rays step through the cell grid (ERT_ACCEL_GRID)
+            if (b == 0) wf_trace_path<true, COUNT, true, true><<<s->wf_grid[4], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else if (b < cells_refill_from && sort) wf_trace_path<false, COUNT, false, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else if (b < cells_refill_from) wf_trace_path<false, COUNT, true, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else wf_trace_path_refill<COUNT, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+        }
+        else if (b == 0) wf_trace_path<true, COUNT, true, false><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b < ERT_WF_REFILL_FROM && sort) wf_trace_path<false, COUNT, false, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT, true, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_path_refill<COUNT, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         // the batch kernels emit their hit records themselves unless the hits are to be binned
-        const bool emitted = !scan && (b == 0 || (b < ERT_WF_REFILL_FROM && !sort));
+        const bool grid_b = cells && b >= cells_from;
+        const bool emitted = !scan && (b == 0 || (b < (grid_b ? cells_refill_from : ERT_WF_REFILL_FROM) && !sort));
         n++;
         TICK(0);
         WF_CHECK("wf_trace_path");
@@ -685,6 +728,8 @@ int finish_slot(ert_scene *s, Slot &sl)
     sl.stats.box_tests = c0[CNT_BOX] + c1[CNT_BOX];
     sl.stats.exact_sphere_tests = c0[CNT_EXACT_SPH] + c1[CNT_EXACT_SPH];
     sl.stats.exact_other_tests = c0[CNT_EXACT_OTHER] + c1[CNT_EXACT_OTHER];
+    sl.stats.cell_steps = c0[CNT_CELL] + c1[CNT_CELL];
+    sl.stats.has_cell_grid = s->host.cgrid.enabled ? 1 : 0;
     sl.stats.path_box_tests = c0[CNT_BOX]; sl.stats.path_filter_tests = c0[CNT_FILTER];
     sl.stats.shadow_box_tests = c1[CNT_BOX]; sl.stats.shadow_filter_tests = c1[CNT_FILTER];
     // per-class device time of the wavefront launches (ERT_FLAG_TIME_KERNELS)
@@ -840,13 +885,14 @@ int ert_render_async(ert_scene *scene, const ert_render_params *params, int slot
     CU(cudaEventRecord(sl.ev0, sl.stream));
     // the wavefront serves the BVH strategy and, past one resident tile of spheres, the brute-force scan
     const bool wf_scan = accel == ERT_ACCEL_LINEAR && scene->host.n_spheres > kWfScanFrom;
-    if (fp.local_rows > 0 && (accel == ERT_ACCEL_BVH || wf_scan) && fp.depth > 0) {
+    const bool wf_cells = accel == ERT_ACCEL_GRID;
+    if (fp.local_rows > 0 && (accel == ERT_ACCEL_BVH || wf_cells || wf_scan) && fp.depth > 0) {
         uint64_t n = 0;
         const bool unsorted = (p.flags & ERT_FLAG_WF_UNSORTED) != 0;
         const bool no_grid = (p.flags & ERT_FLAG_NO_LIGHT_GRID) != 0;
         const bool timed = (p.flags & ERT_FLAG_TIME_KERNELS) != 0;
-        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, &n)
-                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, &n);
+        rc = (p.flags & ERT_FLAG_COUNT_TESTS) ? launch_wavefront<true>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, wf_cells, &n)
+                                              : launch_wavefront<false>(scene, sl, fp, unsorted, no_grid, timed, wf_scan, wf_cells, &n);
         if (rc != ERT_OK) return rc;
         sl.stats.gpu_launches = n;
     } else if (fp.local_rows > 0) {
@@ -926,7 +972,7 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
 {
     if (!scene || (n_rays > 0 && (!rays6 || !order_out || !t_out))) return fail(ERT_ERR_BADARG, "NULL argument");
     if (n_rays < 0) return fail(ERT_ERR_BADARG, "negative ray count");
-    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_BVH_MEGAKERNEL) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_GRID) return fail(ERT_ERR_BADARG, "unknown accel");
     if (n_rays == 0) return ERT_OK;
     std::lock_guard<std::mutex> lock(scene->mu);
     CU(cudaSetDevice(scene->device));
@@ -953,6 +999,7 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
         case ERT_ACCEL_EXACT: trace_rays_kernel<1><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         case ERT_ACCEL_LINEAR: trace_rays_kernel<2><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         case ERT_ACCEL_BVH_MEGAKERNEL: trace_rays_kernel<3><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
+        case ERT_ACCEL_GRID: trace_rays_kernel<5><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         default: trace_rays_kernel<4><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         }
     }

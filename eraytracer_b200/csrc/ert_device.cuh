@@ -59,6 +59,17 @@ struct DevScene {
     // direction grids of the first lg_count lights (light_grid.h): shadow-ray candidates by direction
     const struct LightGridDev *lgrids;
     int lg_count;
+    // uniform cell grid over the spheres (cell_grid.h): path-ray candidates by 3-D DDA
+    struct CellGridDev {
+        const unsigned int *cells;   // [rx*ry*rz] (first_ref << 7) | count
+        const float4 *ref_filter;    // filter spheres in cell order
+        const int *ref_sph;          // ref slot -> sphere index
+        const int *big;              // spheres every ray tests (too large for the cells)
+        int n_big, enabled;
+        int rx, ry, rz;
+        float lo[3], hi[3];
+        float cs, eps;
+    } cg;
 };
 
 // One entry of a light's direction grid: 32 bytes, one 256-bit load.
@@ -86,7 +97,7 @@ struct FrameParams {
     unsigned long long *counters;
 };
 
-enum Counter : int { CNT_RAYS = 0, CNT_FILTER = 1, CNT_BOX = 2, CNT_EXACT_SPH = 3, CNT_EXACT_OTHER = 4, CNT_N = 8 };
+enum Counter : int { CNT_RAYS = 0, CNT_FILTER = 1, CNT_BOX = 2, CNT_EXACT_SPH = 3, CNT_EXACT_OTHER = 4, CNT_CELL = 5, CNT_N = 8 };
 constexpr int kCounterSets = 2;      // [0]: megakernels and wf_trace_path*, [1]: wf_trace_shadow
 
 // ------------------------------------------------------------------ FP64 literal algebra
@@ -186,7 +197,7 @@ __device__ __forceinline__ bool triangle_exact(d3 O, d3 D, const double *tr, dou
 
 template <bool COUNT>
 struct Tally {
-    unsigned int filter = 0, box = 0, exact_sph = 0, exact_other = 0;
+    unsigned int filter = 0, box = 0, exact_sph = 0, exact_other = 0, cell = 0;
 };
 template <>
 struct Tally<false> {};
@@ -640,7 +651,9 @@ __device__ __forceinline__ void flush_counters(const FrameParams &fp, int rays, 
         unsigned int b = __reduce_add_sync(0xffffffffu, tl.box);
         unsigned int c = __reduce_add_sync(0xffffffffu, tl.exact_sph);
         unsigned int d = __reduce_add_sync(0xffffffffu, tl.exact_other);
+        unsigned int e = __reduce_add_sync(0xffffffffu, tl.cell);
         if ((threadIdx.x & 31) == 0) {
+            if (e) atomicAdd(fp.counters + CNT_CELL, (unsigned long long)e);
             if (a) atomicAdd(fp.counters + CNT_FILTER, (unsigned long long)a);
             if (b) atomicAdd(fp.counters + CNT_BOX, (unsigned long long)b);
             if (c) atomicAdd(fp.counters + CNT_EXACT_SPH, (unsigned long long)c);
@@ -824,6 +837,7 @@ render_tiled_kernel(const __grid_constant__ DevScene sc, const __grid_constant__
 }
 
 __device__ void trace_ray_wavefront(const DevScene &sc, d3 O, d3 D, Hit &best);   // ert_wavefront.cuh
+__device__ void trace_ray_grid(const DevScene &sc, d3 O, d3 D, Hit &best);        // ert_wavefront.cuh
 
 // ---- ray batch: nearest_object_intersecting_ray/2 for arbitrary rays (tests, BVH == scan) ----
 template <int ACCEL>
@@ -851,6 +865,10 @@ trace_rays_kernel(const __grid_constant__ DevScene sc, long long n_rays, const d
         // the traversal of the wavefront kernels (ert_wavefront.cuh)
         scan_others<false>(sc, q.O, q.D, q.best, -1, tl);
         if (sc.n_spheres > 0) trace_ray_wavefront(sc, q.O, q.D, q.best);
+    } else if constexpr (ACCEL == 5) {
+        // the cell-grid walk of the wavefront's path kernels (ert_wavefront.cuh)
+        scan_others<false>(sc, q.O, q.D, q.best, -1, tl);
+        if (sc.n_spheres > 0) trace_ray_grid(sc, q.O, q.D, q.best);
     } else {
         resolve_free<ACCEL, false>(sc, q, tl);
     }

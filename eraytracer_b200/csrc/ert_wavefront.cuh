@@ -185,14 +185,15 @@ __device__ __forceinline__ float cullk_from(const SRay &f, double inv_sqrt_a, co
 
 // One leaf sphere: FP32 filter, then the literal FP64 test on survivors (rare).
 template <bool COUNT>
-__device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, const RaySlot &ray, float4 fs, int slot,
-                                            int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
+__device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, const RaySlot &ray, float4 fs,
+                                            const int *__restrict__ slot_sph, int slot, int skip_obj, Hit &best,
+                                            float &cullk, Tally<COUNT> &tl)
 {
     float b, v;
     TALLY(filter);
     if (!filter_stage1(f, fs, b, v)) return;
     if (!filter_stage2(f, fs, b, v, cullk)) return;
-    int sph = __ldg(sc.leaf_sph + slot);
+    int sph = __ldg(slot_sph + slot);
     int code = obj_code(OBJ_SPHERE, sph);
     if (code == skip_obj) return;
     double t;
@@ -292,7 +293,7 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, int *stack, const DevSc
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
             float4 fs = __ldg(sc.leaf_filter + first + k);
-            leaf_sphere<COUNT>(sc, f, ray, fs, first + k, skip_obj, best, tr.cullk, tl);
+            leaf_sphere<COUNT>(sc, f, ray, fs, sc.leaf_sph, first + k, skip_obj, best, tr.cullk, tl);
         }
     }
     if constexpr (ANY) {
@@ -300,6 +301,171 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, int *stack, const DevSc
     }
     trav_pop(tr, stack);
     return tr.node == kTravDone;
+}
+
+// ------------------------------------------------------------------ cell-grid walk (3-D DDA)
+// Path rays of scenes that have a cell grid (cell_grid.h) visit the cells along the ray front to
+// back instead of walking the BVH.  Plane k of an axis sits at lo + k*cs; the ray reaches it at
+// t = k*A + B with A = cs/d, B = (lo - o)/d — one FFMA from the integer-valued float k, so errors do
+// not accumulate and t is monotone in k.  The walk therefore visits exactly the cells of SOME
+// sequence of plane crossings each within a few ulps (of position) of the true one, i.e. at every
+// parameter the true ray is within m/2 of the cell the walk is in (m: the margin of make_sray).
+// The builder lists a sphere in every cell its box inflated by eps overlaps and a ray uses the grid
+// only if 4m <= eps, so every sphere the ray touches is listed in a visited cell; the walk ends
+// when the next cell starts beyond the cull distance of the incumbent (an upper bound, as in the
+// BVH walk) or outside the grid.  Every step moves one plane index towards its end, so the loop
+// ends whatever the float values are.
+struct GridRay {
+    float Ax, Ay, Az, Bx, By, Bz;
+    int sx, sy, sz;                  // signed cell-id strides
+};
+struct GridWalk {
+    float nbx, nby, nbz;             // index of the next plane along each axis (integer-valued)
+    float tx, ty, tz;                // ray parameter there
+    int id;                          // linear cell id; < 0: the walk is over
+    float cullk;
+};
+
+__device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevScene &sc, const SRay &f, float cullk)
+{
+    const DevScene::CellGridDev &cg = sc.cg;
+    g.cullk = cullk;
+    g.id = -1;
+    float t0;
+    if (!slab_test(f, cg.lo[0], cg.hi[0], cg.lo[1], cg.hi[1], cg.lo[2], cg.hi[2], cullk, t0)) return;
+    const float inv_cs = 1.0f / cg.cs;
+    r.Ax = cg.cs * f.ix; r.Ay = cg.cs * f.iy; r.Az = cg.cs * f.iz;
+    r.Bx = __fmaf_rn(cg.lo[0], f.ix, -(f.ox * f.ix));
+    r.By = __fmaf_rn(cg.lo[1], f.iy, -(f.oy * f.iy));
+    r.Bz = __fmaf_rn(cg.lo[2], f.iz, -(f.oz * f.iz));
+    float cx = floorf((__fmaf_rn(f.dx, t0, f.ox) - cg.lo[0]) * inv_cs);
+    float cy = floorf((__fmaf_rn(f.dy, t0, f.oy) - cg.lo[1]) * inv_cs);
+    float cz = floorf((__fmaf_rn(f.dz, t0, f.oz) - cg.lo[2]) * inv_cs);
+    cx = fminf(fmaxf(cx, 0.f), (float)(cg.rx - 1));
+    cy = fminf(fmaxf(cy, 0.f), (float)(cg.ry - 1));
+    cz = fminf(fmaxf(cz, 0.f), (float)(cg.rz - 1));
+    const bool px = f.ix >= 0.f, py = f.iy >= 0.f, pz = f.iz >= 0.f;
+    g.nbx = cx + (px ? 1.f : 0.f); g.nby = cy + (py ? 1.f : 0.f); g.nbz = cz + (pz ? 1.f : 0.f);
+    g.tx = __fmaf_rn(g.nbx, r.Ax, r.Bx); g.ty = __fmaf_rn(g.nby, r.Ay, r.By); g.tz = __fmaf_rn(g.nbz, r.Az, r.Bz);
+    const int sy = cg.rx, sz = cg.rx * cg.ry;
+    r.sx = px ? 1 : -1; r.sy = py ? sy : -sy; r.sz = pz ? sz : -sz;
+    g.id = (int)cx + sy * (int)cy + sz * (int)cz;
+}
+
+// leaves the current cell: the walk is over when the next one starts beyond the cull distance
+__device__ __forceinline__ void grid_advance(GridWalk &g, const GridRay &r, const DevScene::CellGridDev &cg)
+{
+    const float te = fminf(fminf(g.tx, g.ty), g.tz);
+    if (te > g.cullk) { g.id = -1; return; }
+    if (g.tx == te) {
+        const bool pos = r.sx > 0;
+        g.nbx += pos ? 1.f : -1.f;
+        g.tx = __fmaf_rn(g.nbx, r.Ax, r.Bx);
+        g.id += r.sx;
+        if (g.nbx == (pos ? (float)(cg.rx + 1) : -1.f)) g.id = -1;
+    } else if (g.ty == te) {
+        const bool pos = r.sy > 0;
+        g.nby += pos ? 1.f : -1.f;
+        g.ty = __fmaf_rn(g.nby, r.Ay, r.By);
+        g.id += r.sy;
+        if (g.nby == (pos ? (float)(cg.ry + 1) : -1.f)) g.id = -1;
+    } else {
+        const bool pos = r.sz > 0;
+        g.nbz += pos ? 1.f : -1.f;
+        g.tz = __fmaf_rn(g.nbz, r.Az, r.Bz);
+        g.id += r.sz;
+        if (g.nbz == (pos ? (float)(cg.rz + 1) : -1.f)) g.id = -1;
+    }
+}
+
+// Runs empty cells until the ray holds a cell with spheres, tests those and leaves the cell
+// (while-while, like trav_step).  Returns true when the search is over.
+template <bool COUNT>
+__device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
+                                          const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl)
+{
+    const DevScene::CellGridDev &cg = sc.cg;
+    unsigned int c = 0;
+    while (g.id >= 0) {
+        WF_ASSERT(g.id < cg.rx * cg.ry * cg.rz, "cell %d of %d", g.id, cg.rx * cg.ry * cg.rz);
+        c = __ldg(cg.cells + g.id);
+        TALLY(cell);
+        if (c & 127u) break;
+        grid_advance(g, r, cg);
+    }
+    if (g.id < 0) return true;
+    {
+        const int first = (int)(c >> 7), cnt = (int)(c & 127u);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            float4 fs = __ldg(cg.ref_filter + first + k);
+            leaf_sphere<COUNT>(sc, f, ray, fs, cg.ref_sph, first + k, skip_obj, best, g.cullk, tl);
+        }
+    }
+    grid_advance(g, r, cg);
+    return g.id < 0;
+}
+
+// spheres too large for the cells: every ray tests them before its walk
+template <bool COUNT>
+__device__ __forceinline__ void grid_big_spheres(const DevScene &sc, const SRay &f, const RaySlot &ray, int skip_obj,
+                                                 Hit &best, float &cullk, Tally<COUNT> &tl)
+{
+    for (int k = 0; k < sc.cg.n_big; k++) {
+        float4 fs = __ldg(sc.sph_filter + __ldg(sc.cg.big + k));
+        leaf_sphere<COUNT>(sc, f, ray, fs, sc.cg.big, k, skip_obj, best, cullk, tl);
+    }
+}
+
+// A ray whose margin is too large for the grid (origin far outside the scene) walks the BVH
+// instead.  Rare, so it is a call: the walk state of the BVH stays out of the callers' registers.
+__device__ __forceinline__ void walk_bvh_instead(const DevScene *scp, double *slot, int skip_obj, Hit *best_io)
+{
+    const DevScene &sc = *scp;
+    RaySlot ray;
+    ray.p = slot;
+    SRay f;
+    double a, inv;
+    make_sray(sc, ray.O(), ray.D(), f, a, inv);
+    Hit best = *best_io;
+    Tally<false> tl;
+    Trav<false> tr;
+    int stack[kBvhStack];
+    trav_start(tr, stack, f, inv, best);
+    while (!trav_step<false, false>(tr, stack, sc, ray, f, best, skip_obj, -1, tl)) { }
+    *best_io = best;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void grid_trace(const DevScene &sc, const RaySlot &ray, const SRay &f, double inv_sqrt_a,
+                                           int skip_obj, Hit &best, Tally<COUNT> &tl)
+{
+    if (!(f.m4 <= sc.cg.eps)) {
+        Hit tmp = best;
+        walk_bvh_instead(&sc, ray.p, skip_obj, &tmp);
+        best = tmp;
+        return;
+    }
+    float cullk = cullk_from(f, inv_sqrt_a, best);
+    grid_big_spheres<COUNT>(sc, f, ray, skip_obj, best, cullk, tl);
+    GridWalk g;
+    GridRay r;
+    grid_start(g, r, sc, f, cullk);
+    while (!grid_step<COUNT>(g, r, sc, ray, f, best, skip_obj, tl)) { }
+}
+
+// one ray through the cell grid, no persistence (ert_trace_rays with ERT_ACCEL_GRID)
+__device__ void trace_ray_grid(const DevScene &sc, d3 O, d3 D, Hit &best)
+{
+    __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    RaySlot ray;
+    ray.p = &slots[0][threadIdx.x];
+    SRay f;
+    Tally<false> tl;
+    double a, inv;
+    make_sray(sc, O, D, f, a, inv);
+    ray.put(O, D, a, inv);
+    grid_trace<false>(sc, ray, f, inv, -1, best, tl);
 }
 
 // one ray, no persistence (ert_trace_rays); the FP64 ray sits in a local column
@@ -574,7 +740,7 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 // its hits into hit records (what wf_emit_hits does from the result arrays) — the warp is back
 // together after every batch, so the FP64 of the hit location and normal runs on full warps and
 // the results never travel through HBM.
-template <bool FIRST, bool COUNT, bool EMIT>
+template <bool FIRST, bool COUNT, bool EMIT, bool GRID>
 __global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
 wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
               const __grid_constant__ WfBuf wf, int bounce)
@@ -625,10 +791,14 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                                 }
                             }
                         }
-                        Trav<false> tr;
-                        int stack[kBvhStack];
-                        trav_start(tr, stack, f, inv, best);
-                        while (!trav_step<false, COUNT>(tr, stack, sc, ray, f, best, skip, -1, tl)) { }
+                        if constexpr (GRID) {
+                            grid_trace<COUNT>(sc, ray, f, inv, skip, best, tl);
+                        } else {
+                            Trav<false> tr;
+                            int stack[kBvhStack];
+                            trav_start(tr, stack, f, inv, best);
+                            while (!trav_step<false, COUNT>(tr, stack, sc, ray, f, best, skip, -1, tl)) { }
+                        }
                         if (best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
                     }
                 }
@@ -671,7 +841,7 @@ constexpr int kRefillBelow = ERT_WF_REFILL;
 #ifndef ERT_WF_REFILL_MINBLOCKS
 #define ERT_WF_REFILL_MINBLOCKS 4
 #endif
-template <bool COUNT>
+template <bool COUNT, bool GRID>
 __global__ void __launch_bounds__(kWfThreads, ERT_WF_REFILL_MINBLOCKS)
 wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                      const __grid_constant__ WfBuf wf, int bounce)
@@ -693,8 +863,11 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
     Hit best;
     best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
     Trav<false> tr;
-    int stack[kBvhStack];
+    int stack[GRID ? 1 : kBvhStack];
     tr.node = kTravDone; tr.sp = 0; tr.cullk = 0.f;
+    GridWalk gw;
+    GridRay gr;
+    gw.id = -1;
     for (;;) {
         const unsigned int idle = __ballot_sync(0xffffffffu, !have);
         if (32 - __popc(idle) < kRefillBelow && !drained) {
@@ -719,7 +892,20 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                         double a, inv;
                         make_sray(sc, O, D, f, a, inv);
                         ray.put(O, D, a, inv);
-                        trav_start(tr, stack, f, inv, best);
+                        if constexpr (GRID) {
+                            if (f.m4 <= sc.cg.eps) {
+                                float cullk = cullk_from(f, inv, best);
+                                grid_big_spheres<COUNT>(sc, f, ray, -1, best, cullk, tl);
+                                grid_start(gw, gr, sc, f, cullk);
+                            } else {
+                                Hit tmp = best;
+                                walk_bvh_instead(&sc, ray.p, -1, &tmp);
+                                best = tmp;
+                                gw.id = -1;                  // the first step reports the ray as done
+                            }
+                        } else {
+                            trav_start(tr, stack, f, inv, best);
+                        }
                         have = true;
                     } else {
                         wf.res_hit[i] = make_int2(best.obj, best.order);
@@ -734,7 +920,10 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
         }
         for (;;) {
             if (have) {
-                if (trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl)) {
+                bool over;
+                if constexpr (GRID) over = grid_step<COUNT>(gw, gr, sc, ray, f, best, -1, tl);
+                else over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
+                if (over) {
                     __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
                     __stcs(wf.res_t + idx, best.t);
                     have = false;

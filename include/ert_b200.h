@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ERT_ABI_VERSION 2
+#define ERT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ERT_API __attribute__((visibility("default")))
@@ -119,6 +119,10 @@ typedef struct ert_scene_desc {
 #define ERT_ACCEL_BVH     3   /* sphere BVH (FP32 conservative slabs/filter) + FP64 on candidates;
                                * wavefront form: path / shadow / shade queues in HBM, full warps of one ray kind */
 #define ERT_ACCEL_BVH_MEGAKERNEL 4  /* same BVH, one launch, per-pixel state machine (kept as a cross-check) */
+#define ERT_ACCEL_GRID    5   /* the wavefront of ERT_ACCEL_BVH whose path rays step through a uniform cell grid
+                               * over the spheres (3-D DDA, FP32 conservative) instead of walking the BVH.  Built
+                               * for scenes of many small spheres; scenes without one (and rays that start far
+                               * outside the scene) use the BVH.  ERT_ACCEL_AUTO prefers it when the scene has one. */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
 #define ERT_FLAG_TIME_KERNELS  8u  /* ERT_ACCEL_BVH: CUDA events around every launch; fills the *_ms split of ert_stats */
@@ -164,6 +168,10 @@ typedef struct ert_stats {
     uint64_t shadow_box_tests, shadow_filter_tests;   /* wf_trace_shadow: direction grids / BVH walks */
     double path_ms, shadow_ms, other_ms;              /* other: hit emission, binning, shading, finalize */
     uint64_t path_launches, shadow_launches;
+    /* ABI 3 */
+    uint64_t cell_steps;            /* cells visited by the grid walks of path rays (ERT_FLAG_COUNT_TESTS) */
+    int32_t has_cell_grid;          /* the scene has a cell grid (ERT_ACCEL_GRID is available) */
+    int32_t reserved2;
 } ert_stats;
 
 typedef struct ert_scene ert_scene;     /* opaque: device-resident flattened scene */

@@ -1,0 +1,217 @@
+"""GPU parity tests of the cell-grid walk (ERT_ACCEL_GRID): the path rays of the wavefront step
+through a uniform grid over the spheres instead of walking the BVH.  The grid only prunes, so
+every result must equal the linear scan's (raytracer.erl:300-346): same distance bits, same list
+position, bit-identical frames."""
+import numpy as np
+import pytest
+
+import eraytracer_b200 as ert
+from eraytracer_b200 import _lib, multigpu, scene as sc
+from oracle import orc
+from helpers import assert_double_parity, oracle_frame, oracle_scene_from_flat, quantise
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3(gpu):
+    flat = sc.synthetic_scene("c3")
+    dev = flat.upload(0)
+    yield flat, dev
+    dev.close()
+
+
+def random_rays(rng, n, lo, hi):
+    o = np.stack([rng.uniform(lo[a], hi[a], n) for a in range(3)], axis=1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d], axis=1)
+
+
+def test_auto_prefers_the_grid_and_counts_cells(c3):
+    flat, dev = c3
+    frame, st = dev.render(96, 54, 3, fmt="f64", accel="auto", flags=_lib.FLAG_COUNT_TESTS)
+    assert st["accel_used"] == "grid" and st["has_cell_grid"] == 1
+    assert st["cell_steps"] > 96 * 54 and st["path_box_tests"] == 0
+    bvh, sb = dev.render(96, 54, 3, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
+    assert sb["accel_used"] == "bvh" and sb["cell_steps"] == 0 and sb["path_box_tests"] > 0
+    assert np.array_equal(frame, bvh) and st["rays"] == sb["rays"]
+
+
+def test_c3_grid_matches_oracle(c3):
+    flat, dev = c3
+    w, h, depth = 192, 108, 5
+    ref, ref_rays, _ = oracle_frame(flat, w, h, depth)
+    frame, st = dev.render(w, h, depth, fmt="f64", accel="grid")
+    assert st["accel_used"] == "grid"
+    assert_double_parity(frame, ref)
+    assert np.array_equal(quantise(frame), quantise(ref))
+    assert st["rays"] == ref_rays
+
+
+def test_c3_grid_equals_exact_scan_on_gpu(c3):
+    flat, dev = c3
+    w, h, depth = 480, 270, 6
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="exact")
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="grid")
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
+    # row bands of the multi-GPU split
+    out = np.zeros_like(b)
+    for part in range(3):
+        dev.render(w, h, depth, fmt="f64", accel="grid", band_rows=8, n_parts=3, part=part, out=out)
+    assert np.array_equal(out, b)
+
+
+def test_c3_ray_batch_grid_equals_linear_scan(c3):
+    """Distance bits and list position, for rays from inside and outside the grid, rays along
+    the axes, rays that start exactly on cell planes, and rays with zero components."""
+    flat, dev = c3
+    rng = np.random.default_rng(17)
+    rays = [random_rays(rng, 150_000, (-45, -35, -5), (45, 5, 90)),
+            random_rays(rng, 30_000, (-400, -400, -400), (400, 400, 400))]
+    # axis-parallel and planar directions
+    ax = random_rays(rng, 30_000, (-45, -35, -5), (45, 5, 90))
+    k = rng.integers(0, 3, len(ax))
+    ax[:, 3:] = 0.0
+    ax[np.arange(len(ax)), 3 + k] = rng.choice([-1.0, 1.0], len(ax))
+    pl = random_rays(rng, 30_000, (-45, -35, -5), (45, 5, 90))
+    pl[np.arange(len(pl)), 3 + rng.integers(0, 3, len(pl))] = 0.0
+    pl[:, 3:] /= np.maximum(np.linalg.norm(pl[:, 3:], axis=1, keepdims=True), 1e-30)
+    # origins snapped to a lattice that contains the cell planes of any power-of-two-ish edge
+    sn = random_rays(rng, 30_000, (-45, -35, -5), (45, 5, 90))
+    sn[:, :3] = np.round(sn[:, :3] * 4) / 4
+    # un-normalised directions (reflections off un-normalised plane normals, erl:461-480)
+    un = random_rays(rng, 20_000, (-45, -35, -5), (45, 5, 90))
+    un[:, 3:] *= rng.uniform(0.01, 50.0, (len(un), 1))
+    rays += [ax, pl, sn, un]
+    rays = np.concatenate(rays, axis=0)
+    og, tg = dev.trace_rays(rays, accel="grid")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    ob, tb = dev.trace_rays(rays, accel="bvh")
+    assert np.array_equal(og, ol) and np.array_equal(tg, tl)
+    assert np.array_equal(og, ob) and np.array_equal(tg, tb)
+    assert (og >= 0).mean() > 0.2
+    cam, kind, f = oracle_scene_from_flat(flat)
+    oi, ot = orc.nearest_batch(rays[:3000], kind, f)
+    assert np.array_equal(oi, og[:3000]) and np.array_equal(ot, tg[:3000])
+
+
+def stress_scene(n, seed, box, radii, big=0, scale=1.0, offset=(0.0, 0.0, 0.0), float_exact=True):
+    """n small spheres in a box plus `big` large ones, demo floor plane, two lights."""
+    rng = np.random.default_rng(seed)
+    flat = sc.synthetic_scene("c3", n_spheres=n + big, seed=seed)
+    c = np.stack([rng.uniform(-box[a], box[a], n + big) for a in range(3)], axis=1) * scale + np.asarray(offset)
+    r = rng.uniform(radii[0], radii[1], n + big) * scale
+    if big:
+        r[-big:] = rng.uniform(10.0, 40.0, big) * scale
+    if float_exact:
+        c = c.astype(np.float32).astype(np.float64)
+        r = r.astype(np.float32).astype(np.float64)
+    flat.spheres['center'] = c
+    flat.spheres['radius'] = r
+    return flat
+
+
+@pytest.mark.parametrize("case", ("big_spheres", "large_coordinates", "double_centres", "thin_slab", "dense"))
+def test_grid_stress_scenes_equal_linear_scan(gpu, case):
+    if case == "big_spheres":
+        flat = stress_scene(4000, 5, (40, 20, 40), (0.1, 0.6), big=5, offset=(0, -20, 50))
+        lo, hi = (-60, -60, -10), (60, 10, 110)
+    elif case == "large_coordinates":
+        flat = stress_scene(6000, 6, (40, 20, 40), (0.1, 0.8), scale=100.0, offset=(9000.0, -3000.0, 20000.0))
+        lo, hi = (4000, -6000, 15000), (14000, 0, 25000)
+    elif case == "double_centres":
+        flat = stress_scene(5000, 7, (30, 15, 30), (0.05, 0.7), offset=(0.1, -17.3, 40.7), float_exact=False)
+        lo, hi = (-35, -35, 5), (35, 5, 75)
+    elif case == "thin_slab":
+        flat = stress_scene(3000, 8, (50, 0.01, 50), (0.2, 0.5), offset=(0, -3, 60))
+        lo, hi = (-55, -10, 5), (55, 4, 115)
+    else:
+        flat = stress_scene(20000, 9, (6, 6, 6), (0.2, 0.6), offset=(0, -8, 20))
+        lo, hi = (-8, -16, 10), (8, 0, 30)
+    dev = flat.upload(0)
+    rng = np.random.default_rng(3)
+    rays = np.concatenate([random_rays(rng, 60_000, lo, hi),
+                           random_rays(rng, 20_000, [3 * v - 50 for v in lo], [3 * v + 50 for v in hi])], axis=0)
+    # half of the outside rays aim at the scene
+    mid = (np.asarray(lo) + np.asarray(hi)) / 2
+    aim = mid + rng.normal(size=(10_000, 3)) * (np.asarray(hi) - np.asarray(lo)) / 4 - rays[-10_000:, :3]
+    rays[-10_000:, 3:] = aim / np.linalg.norm(aim, axis=1, keepdims=True)
+    og, tg = dev.trace_rays(rays, accel="grid")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    assert np.array_equal(og, ol) and np.array_equal(tg, tl)
+    assert (og >= 0).mean() > 0.05
+    w, h, depth = 160, 90, 4
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="grid")
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
+    if case != "dense":
+        assert sa["accel_used"] == "grid", "the builder should accept this scene"
+    dev.close()
+
+
+def test_far_origins_fall_back_to_the_bvh_walk(c3):
+    """A ray whose FP32 margin exceeds the inflation of the cells (origin far outside the
+    scene) must not use the grid; the result is still the linear scan's."""
+    flat, dev = c3
+    rng = np.random.default_rng(23)
+    n = 20_000
+    target = np.stack([rng.uniform(-40, 40, n), rng.uniform(-30, 4, n), rng.uniform(5, 85, n)], axis=1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dist = 10.0 ** rng.uniform(2, 7, (n, 1))
+    rays = np.concatenate([target - d * dist, d], axis=1)
+    og, tg = dev.trace_rays(rays, accel="grid")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    assert np.array_equal(og, ol) and np.array_equal(tg, tl)
+    assert (og >= 0).sum() > 100
+    # a camera that far away renders through the same fallback
+    cam = sc.pose_camera(0)
+    cam.location[:] = (0.0, -10.0, -3.0e5)
+    cam.fov = 0.02
+    a, sa = dev.render(64, 36, 3, fmt="f64", accel="grid", camera=cam)
+    b, sb = dev.render(64, 36, 3, fmt="f64", accel="exact", camera=cam)
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
+
+
+def test_scenes_without_a_grid_use_the_bvh(gpu):
+    # too few spheres for a grid; ERT_ACCEL_GRID then means the BVH wavefront
+    flat = sc.synthetic_scene("c3", n_spheres=200)
+    dev = flat.upload(0)
+    f, st = dev.render(64, 36, 3, fmt="f64", accel="grid")
+    assert st["accel_used"] == "bvh" and st["has_cell_grid"] == 0
+    e, _ = dev.render(64, 36, 3, fmt="f64", accel="exact")
+    assert np.array_equal(f, e)
+    dev.close()
+    # radii spread over five decades: most spheres would be `big`
+    rng = np.random.default_rng(1)
+    flat = sc.synthetic_scene("c3", n_spheres=3000)
+    flat.spheres['radius'] = (10.0 ** rng.uniform(-2, 3, 3000)).astype(np.float32)
+    dev = flat.upload(0)
+    f, st = dev.render(64, 36, 3, fmt="f64", accel="auto")
+    assert st["accel_used"] == "bvh" and st["has_cell_grid"] == 0
+    e, _ = dev.render(64, 36, 3, fmt="f64", accel="exact")
+    assert np.array_equal(f, e)
+    dev.close()
+
+
+def test_c4_full_4k_grid_equals_bvh(gpu):
+    """Config C4 at full size: the grid frame is the BVH frame, bit for bit (both doubles and RGB8)."""
+    flat = sc.synthetic_scene("c4")
+    dev = flat.upload(0)
+    w, h, depth = 3840, 2160, 5
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="grid")
+    assert sa["accel_used"] == "grid"
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="bvh")
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
+    del b
+    sub = np.zeros_like(a)
+    dev.render(w, h, depth, fmt="f64", accel="linear", band_rows=1, n_parts=1080, part=333, out=sub)
+    rows = multigpu.part_rows(h, 1, 1080, 333)
+    assert np.array_equal(sub[rows], a[rows])
+    rng = np.random.default_rng(12)
+    rays = random_rays(rng, 20000, (-210, -160, -5), (210, 5, 410))
+    og, tg = dev.trace_rays(rays, accel="grid")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    assert np.array_equal(og, ol) and np.array_equal(tg, tl)
+    dev.close()

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libert_b200.so does not export %s" % n
     assert sorted(_lib.EXPORTS) == names
-    assert L.ert_abi_version() == 2
+    assert L.ert_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(tmp_path):
