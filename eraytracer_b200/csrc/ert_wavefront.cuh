@@ -76,6 +76,9 @@ constexpr int kWfThreads = 256;
 #ifndef ERT_WF_MINBLOCKS
 #define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
 #endif
+#ifndef ERT_GRID_MINBLOCKS
+#define ERT_GRID_MINBLOCKS 4        /* the same for the path kernels that walk the cell grid */
+#endif
 #ifndef ERT_WF_SORT_BITS
 #define ERT_WF_SORT_BITS 8
 #endif
@@ -323,6 +326,7 @@ struct GridWalk {
     float nbx, nby, nbz;             // index of the next plane along each axis (integer-valued)
     float tx, ty, tz;                // ray parameter there
     int id;                          // linear cell id; < 0: the walk is over
+    unsigned int c;                  // packed word of cell `id` (fetched one step ahead)
     float cullk;
 };
 
@@ -331,6 +335,7 @@ __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevSce
     const DevScene::CellGridDev &cg = sc.cg;
     g.cullk = cullk;
     g.id = -1;
+    g.c = 0u;
     float t0;
     if (!slab_test(f, cg.lo[0], cg.hi[0], cg.lo[1], cg.hi[1], cg.lo[2], cg.hi[2], cullk, t0)) return;
     const float inv_cs = 1.0f / cg.cs;
@@ -350,13 +355,14 @@ __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevSce
     const int sy = cg.rx, sz = cg.rx * cg.ry;
     r.sx = px ? 1 : -1; r.sy = py ? sy : -sy; r.sz = pz ? sz : -sz;
     g.id = (int)cx + sy * (int)cy + sz * (int)cz;
+    g.c = __ldg(cg.cells + g.id);
 }
 
-// leaves the current cell: the walk is over when the next one starts beyond the cull distance
-__device__ __forceinline__ void grid_advance(GridWalk &g, const GridRay &r, const DevScene::CellGridDev &cg)
+// Moves the walk to the next cell (id < 0 when that is outside the grid) and returns the ray
+// parameter at which the cell just left ends, i.e. where the next one starts.
+__device__ __forceinline__ float grid_advance(GridWalk &g, const GridRay &r, const DevScene::CellGridDev &cg)
 {
     const float te = fminf(fminf(g.tx, g.ty), g.tz);
-    if (te > g.cullk) { g.id = -1; return; }
     if (g.tx == te) {
         const bool pos = r.sx > 0;
         g.nbx += pos ? 1.f : -1.f;
@@ -376,33 +382,85 @@ __device__ __forceinline__ void grid_advance(GridWalk &g, const GridRay &r, cons
         g.id += r.sz;
         if (g.nbz == (pos ? (float)(cg.rz + 1) : -1.f)) g.id = -1;
     }
+    return te;
+}
+
+// The spheres listed in one cell.  The FP32 filter runs over all of them first (survivors as a bit
+// mask), the literal FP64 tests afterwards: lanes of a warp then meet in the expensive part instead
+// of entering it one at a time.  A sphere is listed in every cell it overlaps, so the incumbent
+// itself comes by again: it is skipped.  Once the incumbent has improved inside the cell the
+// remaining survivors go through the filter's distance cull again before their FP64 test.
+template <bool COUNT>
+__device__ __forceinline__ void grid_cell_spheres(const DevScene &sc, const SRay &f, const RaySlot &ray, int first, int cnt,
+                                                  int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
+{
+    const DevScene::CellGridDev &cg = sc.cg;
+#pragma unroll 1
+    for (int base = 0; base < cnt; base += 32) {
+        const int m = min(32, cnt - base);
+        unsigned int surv = 0u;
+        const float4 *fp4 = cg.ref_filter + first + base;
+        float4 fs = __ldg(fp4);
+#pragma unroll 1
+        for (int k = 0; k < m; k++) {
+            const float4 nx = __ldg(fp4 + min(k + 1, m - 1));     // one load ahead of the arithmetic
+            float b, v;
+            TALLY(filter);
+            if (filter_stage1(f, fs, b, v)) {
+                if (filter_stage2(f, fs, b, v, cullk)) surv |= 1u << k;
+            }
+            fs = nx;
+        }
+        bool improved = false;
+        while (surv) {
+            const int k = __ffs((int)surv) - 1;
+            surv &= surv - 1u;
+            const int slot = first + base + k;
+            const int sph = __ldg(cg.ref_sph + slot);
+            const int code = obj_code(OBJ_SPHERE, sph);
+            if (code == skip_obj || code == best.obj) continue;
+            if (improved) {
+                const float4 fs = __ldg(cg.ref_filter + slot);
+                float b, v;
+                if (!filter_stage1(f, fs, b, v) || !filter_stage2(f, fs, b, v, cullk)) continue;
+            }
+            double t;
+            TALLY(exact_sph);
+            if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+                const int ord = sc.sph_order[sph];
+                if (better(t, ord, best)) {
+                    best.t = t; best.order = ord; best.obj = code;
+                    cullk = cullk_from(f, ray.inv_sqrt_a(), best);
+                    improved = true;
+                }
+            }
+        }
+    }
 }
 
 // Runs empty cells until the ray holds a cell with spheres, tests those and leaves the cell
-// (while-while, like trav_step).  Returns true when the search is over.
+// (while-while, like trav_step).  The word of the next cell is fetched before the current one is
+// looked at, so its latency overlaps the step arithmetic and the sphere tests.  Returns true when
+// the search is over: the next cell starts beyond the cull distance, or outside the grid.
 template <bool COUNT>
 __device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
                                           const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
-    unsigned int c = 0;
-    while (g.id >= 0) {
+    unsigned int c;
+    float te;
+    for (;;) {
+        if (g.id < 0) return true;
         WF_ASSERT(g.id < cg.rx * cg.ry * cg.rz, "cell %d of %d", g.id, cg.rx * cg.ry * cg.rz);
-        c = __ldg(cg.cells + g.id);
+        c = g.c;
         TALLY(cell);
+        te = grid_advance(g, r, cg);
+        g.c = g.id >= 0 ? __ldg(cg.cells + g.id) : 0u;
         if (c & 127u) break;
-        grid_advance(g, r, cg);
+        if (te > g.cullk) { g.id = -1; return true; }
     }
-    if (g.id < 0) return true;
-    {
-        const int first = (int)(c >> 7), cnt = (int)(c & 127u);
-#pragma unroll 1
-        for (int k = 0; k < cnt; k++) {
-            float4 fs = __ldg(cg.ref_filter + first + k);
-            leaf_sphere<COUNT>(sc, f, ray, fs, cg.ref_sph, first + k, skip_obj, best, g.cullk, tl);
-        }
-    }
-    grid_advance(g, r, cg);
+    grid_cell_spheres<COUNT>(sc, f, ray, (int)(c >> 7), (int)(c & 127u), skip_obj, best, g.cullk, tl);
+    if (te > g.cullk) g.id = -1;
     return g.id < 0;
 }
 
@@ -741,7 +799,7 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 // together after every batch, so the FP64 of the hit location and normal runs on full warps and
 // the results never travel through HBM.
 template <bool FIRST, bool COUNT, bool EMIT, bool GRID>
-__global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
+__global__ void __launch_bounds__(kWfThreads, GRID ? ERT_GRID_MINBLOCKS : ERT_WF_MINBLOCKS)
 wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
               const __grid_constant__ WfBuf wf, int bounce)
 {
@@ -842,7 +900,7 @@ constexpr int kRefillBelow = ERT_WF_REFILL;
 #define ERT_WF_REFILL_MINBLOCKS 4
 #endif
 template <bool COUNT, bool GRID>
-__global__ void __launch_bounds__(kWfThreads, ERT_WF_REFILL_MINBLOCKS)
+__global__ void __launch_bounds__(kWfThreads, GRID ? ERT_GRID_MINBLOCKS : ERT_WF_REFILL_MINBLOCKS)
 wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                      const __grid_constant__ WfBuf wf, int bounce)
 {
