@@ -77,7 +77,8 @@ constexpr int kWfThreads = 256;
 #define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
 #endif
 #ifndef ERT_GRID_MINBLOCKS
-#define ERT_GRID_MINBLOCKS 4        /* the same for the path kernels that walk the cell grid */
+#define ERT_GRID_MINBLOCKS 3        /* the path kernels that walk the cell grid: 85 registers without spills beat
+                                       64 with (C4 path walks 8.2 vs 9.0 ms) */
 #endif
 #ifndef ERT_WF_SORT_BITS
 #define ERT_WF_SORT_BITS 8
@@ -318,9 +319,28 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, int *stack, const DevSc
 // when the next cell starts beyond the cull distance of the incumbent (an upper bound, as in the
 // BVH walk) or outside the grid.  Every step moves one plane index towards its end, so the loop
 // ends whatever the float values are.
+#ifndef ERT_GRID_RAY_SMEM
+#define ERT_GRID_RAY_SMEM 1          /* the six DDA constants of a ray live in shared memory, not registers */
+#endif
 struct GridRay {
-    float Ax, Ay, Az, Bx, By, Bz;
-    int sx, sy, sz;                  // signed cell-id strides
+#if ERT_GRID_RAY_SMEM
+    float *p;                        // column of this thread, stride kWfThreads: A[3], B[3]
+    __device__ __forceinline__ void bind()
+    {
+        __shared__ float gslots[6][kWfThreads];
+        p = &gslots[0][threadIdx.x];
+    }
+    __device__ __forceinline__ float A(int k) const { return p[k * kWfThreads]; }
+    __device__ __forceinline__ float B(int k) const { return p[(3 + k) * kWfThreads]; }
+    __device__ __forceinline__ void set(int k, float a, float b) { p[k * kWfThreads] = a; p[(3 + k) * kWfThreads] = b; }
+#else
+    float a_[3], b_[3];
+    __device__ __forceinline__ void bind() { }
+    __device__ __forceinline__ float A(int k) const { return a_[k]; }
+    __device__ __forceinline__ float B(int k) const { return b_[k]; }
+    __device__ __forceinline__ void set(int k, float a, float b) { a_[k] = a; b_[k] = b; }
+#endif
+    int sgn;                         // bit k set: the ray runs towards +k
 };
 struct GridWalk {
     float nbx, nby, nbz;             // index of the next plane along each axis (integer-valued)
@@ -339,10 +359,12 @@ __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevSce
     float t0;
     if (!slab_test(f, cg.lo[0], cg.hi[0], cg.lo[1], cg.hi[1], cg.lo[2], cg.hi[2], cullk, t0)) return;
     const float inv_cs = 1.0f / cg.cs;
-    r.Ax = cg.cs * f.ix; r.Ay = cg.cs * f.iy; r.Az = cg.cs * f.iz;
-    r.Bx = __fmaf_rn(cg.lo[0], f.ix, -(f.ox * f.ix));
-    r.By = __fmaf_rn(cg.lo[1], f.iy, -(f.oy * f.iy));
-    r.Bz = __fmaf_rn(cg.lo[2], f.iz, -(f.oz * f.iz));
+    r.bind();
+    const float Ax = cg.cs * f.ix, Ay = cg.cs * f.iy, Az = cg.cs * f.iz;
+    const float Bx = __fmaf_rn(cg.lo[0], f.ix, -(f.ox * f.ix));
+    const float By = __fmaf_rn(cg.lo[1], f.iy, -(f.oy * f.iy));
+    const float Bz = __fmaf_rn(cg.lo[2], f.iz, -(f.oz * f.iz));
+    r.set(0, Ax, Bx); r.set(1, Ay, By); r.set(2, Az, Bz);
     float cx = floorf((__fmaf_rn(f.dx, t0, f.ox) - cg.lo[0]) * inv_cs);
     float cy = floorf((__fmaf_rn(f.dy, t0, f.oy) - cg.lo[1]) * inv_cs);
     float cz = floorf((__fmaf_rn(f.dz, t0, f.oz) - cg.lo[2]) * inv_cs);
@@ -351,9 +373,9 @@ __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevSce
     cz = fminf(fmaxf(cz, 0.f), (float)(cg.rz - 1));
     const bool px = f.ix >= 0.f, py = f.iy >= 0.f, pz = f.iz >= 0.f;
     g.nbx = cx + (px ? 1.f : 0.f); g.nby = cy + (py ? 1.f : 0.f); g.nbz = cz + (pz ? 1.f : 0.f);
-    g.tx = __fmaf_rn(g.nbx, r.Ax, r.Bx); g.ty = __fmaf_rn(g.nby, r.Ay, r.By); g.tz = __fmaf_rn(g.nbz, r.Az, r.Bz);
+    g.tx = __fmaf_rn(g.nbx, Ax, Bx); g.ty = __fmaf_rn(g.nby, Ay, By); g.tz = __fmaf_rn(g.nbz, Az, Bz);
     const int sy = cg.rx, sz = cg.rx * cg.ry;
-    r.sx = px ? 1 : -1; r.sy = py ? sy : -sy; r.sz = pz ? sz : -sz;
+    r.sgn = (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
     g.id = (int)cx + sy * (int)cy + sz * (int)cz;
     g.c = __ldg(cg.cells + g.id);
 }
@@ -364,104 +386,140 @@ __device__ __forceinline__ float grid_advance(GridWalk &g, const GridRay &r, con
 {
     const float te = fminf(fminf(g.tx, g.ty), g.tz);
     if (g.tx == te) {
-        const bool pos = r.sx > 0;
+        const bool pos = (r.sgn & 1) != 0;
         g.nbx += pos ? 1.f : -1.f;
-        g.tx = __fmaf_rn(g.nbx, r.Ax, r.Bx);
-        g.id += r.sx;
+        g.tx = __fmaf_rn(g.nbx, r.A(0), r.B(0));
+        g.id += pos ? 1 : -1;
         if (g.nbx == (pos ? (float)(cg.rx + 1) : -1.f)) g.id = -1;
     } else if (g.ty == te) {
-        const bool pos = r.sy > 0;
+        const bool pos = (r.sgn & 2) != 0;
         g.nby += pos ? 1.f : -1.f;
-        g.ty = __fmaf_rn(g.nby, r.Ay, r.By);
-        g.id += r.sy;
+        g.ty = __fmaf_rn(g.nby, r.A(1), r.B(1));
+        g.id += pos ? cg.rx : -cg.rx;
         if (g.nby == (pos ? (float)(cg.ry + 1) : -1.f)) g.id = -1;
     } else {
-        const bool pos = r.sz > 0;
+        const bool pos = (r.sgn & 4) != 0;
         g.nbz += pos ? 1.f : -1.f;
-        g.tz = __fmaf_rn(g.nbz, r.Az, r.Bz);
-        g.id += r.sz;
+        g.tz = __fmaf_rn(g.nbz, r.A(2), r.B(2));
+        g.id += pos ? cg.rx * cg.ry : -(cg.rx * cg.ry);
         if (g.nbz == (pos ? (float)(cg.rz + 1) : -1.f)) g.id = -1;
     }
     return te;
 }
 
-// The spheres listed in one cell.  The FP32 filter runs over all of them first (survivors as a bit
-// mask), the literal FP64 tests afterwards: lanes of a warp then meet in the expensive part instead
-// of entering it one at a time.  A sphere is listed in every cell it overlaps, so the incumbent
-// itself comes by again: it is skipped.  Once the incumbent has improved inside the cell the
-// remaining survivors go through the filter's distance cull again before their FP64 test.
+// The spheres listed in one cell, in two phases.  grid_filter runs the FP32 filter over up to 32 of
+// them (survivors as a bit mask), grid_exact the literal FP64 tests of the survivors: callers put the
+// second phase where the lanes of a warp meet again, so that they enter the expensive part together
+// instead of one at a time.  A sphere is listed in every cell it overlaps, so the incumbent itself
+// comes by again: it is skipped.  Once the incumbent has improved inside the cell the remaining
+// survivors go through the filter's distance cull again before their FP64 test.
 template <bool COUNT>
-__device__ __forceinline__ void grid_cell_spheres(const DevScene &sc, const SRay &f, const RaySlot &ray, int first, int cnt,
-                                                  int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
+__device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SRay &f, int first, int cnt, float cullk,
+                                                    Tally<COUNT> &tl)
+{
+    const float4 *fp4 = sc.cg.ref_filter + first;
+    unsigned int surv = 0u;
+    float4 s0 = __ldg(fp4), s1 = __ldg(fp4 + min(1, cnt - 1));
+#pragma unroll 1
+    for (int k = 0; k < cnt; k += 2) {
+        // two spheres per round, the next two already in flight
+        const float4 n0 = __ldg(fp4 + min(k + 2, cnt - 1)), n1 = __ldg(fp4 + min(k + 3, cnt - 1));
+        float b, v;
+        if constexpr (COUNT) tl.filter += (k + 1 < cnt) ? 2 : 1;
+        if (filter_stage1(f, s0, b, v)) {
+            if (filter_stage2(f, s0, b, v, cullk)) surv |= 1u << k;
+        }
+        if (filter_stage1(f, s1, b, v) && k + 1 < cnt) {
+            if (filter_stage2(f, s1, b, v, cullk)) surv |= 2u << k;
+        }
+        s0 = n0; s1 = n1;
+    }
+    return surv;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
+                                           unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
-#pragma unroll 1
-    for (int base = 0; base < cnt; base += 32) {
-        const int m = min(32, cnt - base);
-        unsigned int surv = 0u;
-        const float4 *fp4 = cg.ref_filter + first + base;
-        float4 fs = __ldg(fp4);
-#pragma unroll 1
-        for (int k = 0; k < m; k++) {
-            const float4 nx = __ldg(fp4 + min(k + 1, m - 1));     // one load ahead of the arithmetic
+    bool improved = false;
+    while (surv) {
+        const int k = __ffs((int)surv) - 1;
+        surv &= surv - 1u;
+        const int slot = first + k;
+        const int sph = __ldg(cg.ref_sph + slot);
+        const int code = obj_code(OBJ_SPHERE, sph);
+        if (code == skip_obj || code == best.obj) continue;
+        if (improved) {
+            const float4 fs = __ldg(cg.ref_filter + slot);
             float b, v;
-            TALLY(filter);
-            if (filter_stage1(f, fs, b, v)) {
-                if (filter_stage2(f, fs, b, v, cullk)) surv |= 1u << k;
-            }
-            fs = nx;
+            if (!filter_stage1(f, fs, b, v) || !filter_stage2(f, fs, b, v, cullk)) continue;
         }
-        bool improved = false;
-        while (surv) {
-            const int k = __ffs((int)surv) - 1;
-            surv &= surv - 1u;
-            const int slot = first + base + k;
-            const int sph = __ldg(cg.ref_sph + slot);
-            const int code = obj_code(OBJ_SPHERE, sph);
-            if (code == skip_obj || code == best.obj) continue;
-            if (improved) {
-                const float4 fs = __ldg(cg.ref_filter + slot);
-                float b, v;
-                if (!filter_stage1(f, fs, b, v) || !filter_stage2(f, fs, b, v, cullk)) continue;
-            }
-            double t;
-            TALLY(exact_sph);
-            if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
-                const int ord = sc.sph_order[sph];
-                if (better(t, ord, best)) {
-                    best.t = t; best.order = ord; best.obj = code;
-                    cullk = cullk_from(f, ray.inv_sqrt_a(), best);
-                    improved = true;
-                }
+        double t;
+        TALLY(exact_sph);
+        if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+            const int ord = sc.sph_order[sph];
+            if (better(t, ord, best)) {
+                best.t = t; best.order = ord; best.obj = code;
+                cullk = cullk_from(f, ray.inv_sqrt_a(), best);
+                improved = true;
             }
         }
     }
 }
 
-// Runs empty cells until the ray holds a cell with spheres, tests those and leaves the cell
-// (while-while, like trav_step).  The word of the next cell is fetched before the current one is
-// looked at, so its latency overlaps the step arithmetic and the sphere tests.  Returns true when
-// the search is over: the next cell starts beyond the cull distance, or outside the grid.
+// Runs empty cells until the ray holds a cell with spheres and filters those (while-while, like
+// trav_step).  The word of the next cell is fetched before the current one is looked at, so its
+// latency overlaps the step arithmetic and the sphere tests.  Returns false when the walk is over
+// (the next cell starts beyond the cull distance, or outside the grid); otherwise `surv` marks the
+// filter survivors among the spheres from slot `first` on and `te` is where the cell ends:
+// grid_exact on the survivors and grid_leave complete the step.
 template <bool COUNT>
-__device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
-                                          const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl)
+__device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
+                                          const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl, unsigned int &surv,
+                                          int &first, float &te)
 {
     const DevScene::CellGridDev &cg = sc.cg;
     unsigned int c;
-    float te;
+    surv = 0u;
     for (;;) {
-        if (g.id < 0) return true;
+        if (g.id < 0) return false;
         WF_ASSERT(g.id < cg.rx * cg.ry * cg.rz, "cell %d of %d", g.id, cg.rx * cg.ry * cg.rz);
         c = g.c;
         TALLY(cell);
         te = grid_advance(g, r, cg);
         g.c = g.id >= 0 ? __ldg(cg.cells + g.id) : 0u;
         if (c & 127u) break;
-        if (te > g.cullk) { g.id = -1; return true; }
+        if (te > g.cullk) { g.id = -1; return false; }
     }
-    grid_cell_spheres<COUNT>(sc, f, ray, (int)(c >> 7), (int)(c & 127u), skip_obj, best, g.cullk, tl);
+    first = (int)(c >> 7);
+    int cnt = (int)(c & 127u);
+    while (cnt > 32) {
+        // rare: more than one mask's worth of spheres in the cell; all but the last 32 are finished here
+        const unsigned int sv = grid_filter<COUNT>(sc, f, first, 32, g.cullk, tl);
+        grid_exact<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
+        first += 32; cnt -= 32;
+    }
+    surv = grid_filter<COUNT>(sc, f, first, cnt, g.cullk, tl);
+    return true;
+}
+__device__ __forceinline__ bool grid_leave(GridWalk &g, float te)
+{
     if (te > g.cullk) g.id = -1;
     return g.id < 0;
+}
+
+// one whole step for callers that do not separate the phases; returns true when the search is over
+template <bool COUNT>
+__device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
+                                          const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl)
+{
+    unsigned int surv;
+    int first;
+    float te;
+    if (!grid_find<COUNT>(g, r, sc, ray, f, best, skip_obj, tl, surv, first, te)) return true;
+    grid_exact<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
+    return grid_leave(g, te);
 }
 
 // spheres too large for the cells: every ray tests them before its walk
@@ -494,21 +552,32 @@ __device__ __forceinline__ void walk_bvh_instead(const DevScene *scp, double *sl
     *best_io = best;
 }
 
+// Sets a ray up for the grid: the spheres too large for the cells, then the start of the walk.
+// Returns false when there is no walk to make (also for rays that had to walk the BVH instead).
 template <bool COUNT>
-__device__ __forceinline__ void grid_trace(const DevScene &sc, const RaySlot &ray, const SRay &f, double inv_sqrt_a,
-                                           int skip_obj, Hit &best, Tally<COUNT> &tl)
+__device__ __forceinline__ bool grid_begin(GridWalk &g, GridRay &r, const DevScene &sc, const RaySlot &ray, const SRay &f,
+                                           double inv_sqrt_a, int skip_obj, Hit &best, Tally<COUNT> &tl)
 {
+    g.id = -1;
     if (!(f.m4 <= sc.cg.eps)) {
         Hit tmp = best;
         walk_bvh_instead(&sc, ray.p, skip_obj, &tmp);
         best = tmp;
-        return;
+        return false;
     }
     float cullk = cullk_from(f, inv_sqrt_a, best);
     grid_big_spheres<COUNT>(sc, f, ray, skip_obj, best, cullk, tl);
+    grid_start(g, r, sc, f, cullk);
+    return g.id >= 0;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void grid_trace(const DevScene &sc, const RaySlot &ray, const SRay &f, double inv_sqrt_a,
+                                           int skip_obj, Hit &best, Tally<COUNT> &tl)
+{
     GridWalk g;
     GridRay r;
-    grid_start(g, r, sc, f, cullk);
+    if (!grid_begin<COUNT>(g, r, sc, ray, f, inv_sqrt_a, skip_obj, best, tl)) return;
     while (!grid_step<COUNT>(g, r, sc, ray, f, best, skip_obj, tl)) { }
 }
 
@@ -824,18 +893,21 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
             int pid = 0;
             Hit best;
             best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+            SRay f;
+            GridWalk gw;
+            GridRay gr;
+            bool walking = false, searched = false;
+            int skip = -1;
             if (in_range) {
                 d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
                 path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
                 if (valid) {
                     rays++;
                     scan_others<COUNT>(sc, O, D, best, -1, tl);
-                    SRay f;
                     double a, inv;
                     make_sray(sc, O, D, f, a, inv);
                     ray.put(O, D, a, inv);
                     if (sc.n_spheres > 0) {
-                        int skip = -1;
                         if (hint >= 0) {
                             // seed the search with the previous ray's sphere: a real candidate of the
                             // scan, so the minimum over (t, order) is unchanged
@@ -850,17 +922,32 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                             }
                         }
                         if constexpr (GRID) {
-                            grid_trace<COUNT>(sc, ray, f, inv, skip, best, tl);
+                            walking = grid_begin<COUNT>(gw, gr, sc, ray, f, inv, skip, best, tl);
                         } else {
                             Trav<false> tr;
                             int stack[kBvhStack];
                             trav_start(tr, stack, f, inv, best);
                             while (!trav_step<false, COUNT>(tr, stack, sc, ray, f, best, skip, -1, tl)) { }
                         }
-                        if (best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
+                        searched = true;
                     }
                 }
             }
+            if constexpr (GRID) {
+                // the lanes of the batch walk to their next cell with spheres and filter them on their own,
+                // then meet for the FP64 tests of the survivors
+                while (__any_sync(0xffffffffu, walking)) {
+                    unsigned int surv = 0u;
+                    int first = 0;
+                    float te = 0.f;
+                    bool found = false;
+                    if (walking) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, skip, tl, surv, first, te);
+                    __syncwarp();
+                    if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
+                    if (walking) walking = found ? !grid_leave(gw, te) : false;
+                }
+            }
+            if (searched && best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
             if constexpr (!EMIT) {
                 if (in_range) {
                     __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
@@ -977,15 +1064,25 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
             continue;
         }
         for (;;) {
-            if (have) {
-                bool over;
-                if constexpr (GRID) over = grid_step<COUNT>(gw, gr, sc, ray, f, best, -1, tl);
-                else over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
-                if (over) {
-                    __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
-                    __stcs(wf.res_t + idx, best.t);
-                    have = false;
-                }
+            bool over = false;
+            if constexpr (GRID) {
+                // the lanes walk to their next cell with spheres and filter them on their own, then meet
+                // for the FP64 tests of the survivors
+                unsigned int surv = 0u;
+                int first = 0;
+                float te = 0.f;
+                bool found = false;
+                if (have) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, -1, tl, surv, first, te);
+                __syncwarp();
+                if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
+                if (have) over = found ? grid_leave(gw, te) : true;
+            } else {
+                if (have) over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
+            }
+            if (over) {
+                __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
+                __stcs(wf.res_t + idx, best.t);
+                have = false;
             }
             const int act = __popc(__ballot_sync(0xffffffffu, have));
             if (act == 0 || (!drained && act < kRefillBelow)) break;

@@ -7,6 +7,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/full
 for w in c4 c3 c2 c2d5 c5; do
   timeout 600 python bench.py --workload $w > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err || { echo "bench $w failed"; tail -5 gpurun_out/bench_$w.err; }
 done
+timeout 600 python bench.py --workload c4 --accel bvh > gpurun_out/bench_c4_bvh.json 2> gpurun_out/bench_c4_bvh.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_c4.json 2> gpurun_out/bench_ref_c4.err
 python - <<PY
 import json,glob
