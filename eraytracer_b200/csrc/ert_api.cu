@@ -347,11 +347,26 @@ int upload_scene(ert_scene *s)
                 c.cx = G.fs[4 * e]; c.cy = G.fs[4 * e + 1]; c.cz = G.fs[4 * e + 2]; c.R = G.fs[4 * e + 3];
                 c.sphere = G.entries[e].sphere; c.dmin = G.entries[e].dmin; c.pad[0] = c.pad[1] = 0;
             }
-            const unsigned int *off; const LightGridCand *cd; const int *al;
+            // per-cell heads: the nearest candidate inline, the rest by range
+            const size_t n_cells = G.cell_off.empty() ? 0 : G.cell_off.size() - 1;
+            std::vector<LightGridCand> head(n_cells);
+            for (size_t c = 0; c < n_cells; c++) {
+                const uint32_t e0 = G.cell_off[c], e1 = G.cell_off[c + 1];
+                LightGridCand &hd = head[c];
+                if (e0 < e1) {
+                    hd = cand[e0];
+                    hd.pad[0] = (int)(e0 + 1); hd.pad[1] = (int)e1;
+                } else {
+                    hd.cx = hd.cy = hd.cz = 0.f; hd.R = -3.0e38f; hd.sphere = -1; hd.dmin = INFINITY;
+                    hd.pad[0] = hd.pad[1] = 0;
+                }
+            }
+            const unsigned int *off; const LightGridCand *cd; const LightGridCand *hd; const int *al;
             if ((rc = upload<unsigned int>(s, G.cell_off, &off)) != ERT_OK) return rc;
             if ((rc = upload<LightGridCand>(s, cand, &cd)) != ERT_OK) return rc;
+            if ((rc = upload<LightGridCand>(s, head, &hd)) != ERT_OK) return rc;
             if ((rc = upload<int>(s, G.always, &al)) != ERT_OK) return rc;
-            lg[g].cell_off = off; lg[g].cand = cd; lg[g].always = al;
+            lg[g].cell_off = off; lg[g].cand = cd; lg[g].head = hd; lg[g].always = al;
             lg[g].n_always = (int)G.always.size(); lg[g].res = G.res;
         }
         const LightGridDev *lgd;

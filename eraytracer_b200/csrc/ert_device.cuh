@@ -81,6 +81,9 @@ struct alignas(32) LightGridCand {
 };
 struct LightGridDev {
     const unsigned int *cell_off;    // [6*res*res + 1]
+    const LightGridCand *head;       // [6*res*res] the first (nearest) candidate of every cell, its pad[] holding
+                                     // the range [pad[0], pad[1]) of the remaining ones in `cand`; an empty cell
+                                     // has dmin = +inf: one fetch per shadow ray instead of offsets, then entry
     const LightGridCand *cand;       // nearest first inside a cell
     const int *always;               // spheres that contain the light: candidates of every ray
     int n_always;

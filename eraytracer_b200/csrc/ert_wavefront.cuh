@@ -76,6 +76,9 @@ constexpr int kWfThreads = 256;
 #ifndef ERT_WF_MINBLOCKS
 #define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
 #endif
+#ifndef ERT_SHADOW_MINBLOCKS
+#define ERT_SHADOW_MINBLOCKS 4      /* the shadow kernel */
+#endif
 #ifndef ERT_GRID_MINBLOCKS
 #define ERT_GRID_MINBLOCKS 3        /* the path kernels that walk the cell grid: 85 registers without spills beat
                                        64 with (C4 path walks 8.2 vs 9.0 ms) */
@@ -159,6 +162,7 @@ __device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &
     f.khx = -(f.ox - m) * f.ix; f.khy = -(f.oy - m) * f.iy; f.khz = -(f.oz - m) * f.iz;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void ldg256(const void *p, float (&v)[8])
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -780,20 +784,27 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
 {
     const float cull0 = cullk_from(f, inv_sqrt_a, best);
     const unsigned int cell = light_grid_cell_dev(D, lg.res);
-    const unsigned int e0 = __ldg(lg.cell_off + cell), e1 = __ldg(lg.cell_off + cell + 1);
-    for (unsigned int e = e0; e < e1; e++) {
-        float c[8];
-        ldg256(lg.cand + e, c);
+    // the head of the cell carries its nearest candidate and the range of the others: one dependent
+    // fetch for the rays that the first candidate settles (most of them)
+    float c[8];
+    ldg256(lg.head + cell, c);
+    unsigned int e = __float_as_uint(c[6]);
+    const unsigned int e1 = __float_as_uint(c[7]);
+    for (;;) {
         if (c[5] > cull0) break;                         // this and all later candidates lie beyond the target
         const float4 fs = make_float4(c[0], c[1], c[2], c[3]);
         const int sph = __float_as_int(c[4]);
+        const bool more = e < e1;
+        if (more) ldg256(lg.cand + e, c);                // in flight while this candidate is tested
+        e++;
         float fb, fv;
         TALLY(filter);
-        if (!filter_stage1(f, fs, fb, fv) || !filter_stage2(f, fs, fb, fv, cull0)) continue;
-        if (obj_code(OBJ_SPHERE, sph) == target) continue;
-        double th;
-        TALLY(exact_sph);
-        if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+        if (filter_stage1(f, fs, fb, fv) && filter_stage2(f, fs, fb, fv, cull0) && obj_code(OBJ_SPHERE, sph) != target) {
+            double th;
+            TALLY(exact_sph);
+            if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+        }
+        if (!more) break;
     }
     for (int k = 0; k < lg.n_always; k++) {
         const int sph = lg.always[k];
@@ -1140,7 +1151,7 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
 // (t, order) settles the question (erl:263), so a neighbour's occluder usually ends the query
 // without a walk.
 template <bool COUNT, bool USE_GRID>
-__global__ void __launch_bounds__(kWfThreads, ERT_WF_MINBLOCKS)
+__global__ void __launch_bounds__(kWfThreads, ERT_SHADOW_MINBLOCKS)
 wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                 const __grid_constant__ WfBuf wf, int bounce)
 {
@@ -1185,9 +1196,13 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             bool lit = false;
             {
                 const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+                // the next batch's record (same light, 32 hits on) and this target's FP64 sphere: on their
+                // way to L1 while the direction is normalised
+                if (h + 32u < n_hits) prefetch_l1(wf.hit_head + h + 32u);
                 d3 P = mk(r0.x, r0.y, r0.z);
                 const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
                 const int order = (int)(__double_as_longlong(r0.w) >> 32);
+                if (obj_type(target) == OBJ_SPHERE) prefetch_l1(sc.sph_exact + obj_index(target));
                 const double *lt = sc.lights + 9 * (size_t)l;
                 d3 O = mk(lt[3], lt[4], lt[5]);
                 d3 D = vnormalize(vsub(P, O));                     // erl:257-260
