@@ -44,6 +44,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+# stdout whatever NCCL_DEBUG_FILE says when stderr is a file), so file descriptor 1 is pointed at stderr for
+# the whole run and the result line goes to the saved original.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def build_scene(kind):
     from eraytracer_b200 import scene as sc
     if kind == "demo":
@@ -199,7 +222,7 @@ def reference_arm(args, rank):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -458,7 +481,7 @@ def gpu_arm(args, rank, world, local_rank):
                 "value": c_rays / c_dt / 1e6, "unit": "Mrays/s", "cores": arm.cores, "kind": "port",
                 "sample": "%dx%d pixel lattice (%d px) of the %dx%d frame, %.1f s" % (nx, ny, c_px, w, h, c_dt),
                 "note": "C restatement of raytracer.erl (oracle/oracle.c), not BEAM: Erlang/OTP is not installed"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
 
     barrier()
     for hst in hosts:
@@ -480,6 +503,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sample at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
