@@ -76,6 +76,9 @@ constexpr int kWfThreads = 256;
 #ifndef ERT_WF_MINBLOCKS
 #define ERT_WF_MINBLOCKS 4          /* resident blocks per SM the traversal kernels are compiled for */
 #endif
+#ifndef ERT_SHADE_MINBLOCKS
+#define ERT_SHADE_MINBLOCKS 3       /* wf_shade */
+#endif
 #ifndef ERT_SHADOW_MINBLOCKS
 #define ERT_SHADOW_MINBLOCKS 4      /* the shadow kernel */
 #endif
@@ -1116,31 +1119,47 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
     const unsigned int n_warps = (gridDim.x * kWfThreads) >> 5;
     HitHead *out_head = SORT ? wf.raw_head : wf.hit_head;
     HitTail *out_tail = SORT ? wf.raw_tail : wf.hit_tail;
-    for (unsigned long long base = (unsigned long long)warp * 32; base < n; base += (unsigned long long)n_warps * 32) {
-        unsigned int i = (unsigned int)base + lane;
-        int2 r = make_int2(-1, 0);
-        if (i < n) r = wf.res_hit[i];
-        bool hit = r.x >= 0;
-        unsigned int m = __ballot_sync(0xffffffffu, hit);
-        if (!m) continue;
+    // A warp takes kEmitBatches batches of 32 entries per round and reserves their hit slots with ONE
+    // atomic: every warp of the grid adds to the same counter, and at one atomic per 32 entries the
+    // launch waited on that address more than on memory.
+    constexpr int kEmitBatches = 4;
+    for (unsigned long long base = (unsigned long long)warp * (32 * kEmitBatches); base < n;
+         base += (unsigned long long)n_warps * (32 * kEmitBatches)) {
+        int2 r[kEmitBatches];
+        unsigned int m[kEmitBatches];
+        unsigned int total = 0;
+#pragma unroll
+        for (int k = 0; k < kEmitBatches; k++) {
+            const unsigned long long i64 = base + (unsigned long long)(32 * k + lane);
+            r[k] = make_int2(-1, 0);
+            if (i64 < n) r[k] = wf.res_hit[(unsigned int)i64];
+            m[k] = __ballot_sync(0xffffffffu, r[k].x >= 0);
+            total += __popc(m[k]);
+        }
+        if (!total) continue;
         unsigned int slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)__popc(m));
+        if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, total);
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (hit) {
-            d3 O, D;
-            int pid;
-            bool valid;
-            path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
-            double t = wf.res_t[i];
-            d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
-            d3 N = hit_normal(sc, r.x, P);
-            size_t s = slot0 + rank_in(m, lane);
-            write_hit(out_head, out_tail, s, P, N, D, r.x, r.y, pid);
-            if constexpr (SORT) {
-                unsigned int key = sort_cell(sc, P);
-                wf.r_key[s] = key;
-                atomicAdd(wf.hist + key, 1u);
+#pragma unroll
+        for (int k = 0; k < kEmitBatches; k++) {
+            if (r[k].x >= 0) {
+                const unsigned int i = (unsigned int)base + (unsigned int)(32 * k + lane);
+                d3 O, D;
+                int pid;
+                bool valid;
+                path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
+                double t = wf.res_t[i];
+                d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
+                d3 N = hit_normal(sc, r[k].x, P);
+                size_t s = slot0 + rank_in(m[k], lane);
+                write_hit(out_head, out_tail, s, P, N, D, r[k].x, r[k].y, pid);
+                if constexpr (SORT) {
+                    unsigned int key = sort_cell(sc, P);
+                    wf.r_key[s] = key;
+                    atomicAdd(wf.hist + key, 1u);
+                }
             }
+            slot0 += __popc(m[k]);
         }
     }
 }
@@ -1340,37 +1359,49 @@ __device__ __forceinline__ void scan_all_tiles(const DevScene &sc, ScanPipe &pp,
     __syncthreads();                                      // the buffers are free for the next batch
 }
 
-// The filter over one tile for one ray.  Groups of kScanGroup spheres are tested branch-free (the
-// pass bits collect in a mask, so the loads and FMAs of a group overlap); survivors — a few per
-// thousand — then go through stage 2 and the literal FP64 test.
-constexpr int kScanGroup = 8;
+// The filter over one tile for one ray.  A group of kScanGroup spheres costs 10 FP32-pipe
+// instructions and one LDS.128 per sphere plus ONE 3-input max per two spheres: the group keeps only
+// the largest stage-1 value v, and one compare per group decides whether any of its spheres can
+// pass (v >= -theta).  Only then — a few groups per thousand — are its spheres looked at one by one
+// (stage 1 again, stage 2, literal FP64 test).  fmaxf drops NaNs, and the filter must pass them
+// (DESIGN.md "Filter bounds"), so a ray for which v could overflow to Inf - Inf takes every group the
+// slow way (`m0` = +Inf): coordinates beyond 1e17, never in practice.
+#ifndef ERT_SCAN_GROUP
+#define ERT_SCAN_GROUP 16
+#endif
+constexpr int kScanGroup = ERT_SCAN_GROUP;
+static_assert(kScanGroup % 2 == 0 && kScanTile % kScanGroup == 0, "groups are whole pairs and tile whole groups");
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, const RaySlot &ray, const float4 *tile,
                                           int cnt, int base, int skip_obj, int seed_obj, Hit &best, float &cullk,
                                           bool &active, Tally<COUNT> &tl)
 {
-    const float nbcull = -f.bcull, ntheta = -f.theta;
+    const float ntheta = -f.theta;
+    const float oabs = fmaxf(fmaxf(fabsf(f.ox), fabsf(f.oy)), fabsf(f.oz));
+    const float m0 = (oabs + sc.abs_max < 1e17f) ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
 #pragma unroll 1
     for (int k0 = 0; k0 < cnt; k0 += kScanGroup) {
-        unsigned int mask = 0;
+        float m = m0;
 #pragma unroll
-        for (int u = 0; u < kScanGroup; u++) {
-            const float4 fs = tile[k0 + u];              // past `cnt` the buffer holds stale spheres: masked below
-            const float cx = fs.x - f.ox, cy = fs.y - f.oy, cz = fs.z - f.oz;
-            const float b = __fmaf_rn(f.dz, cz, __fmaf_rn(f.dy, cy, f.dx * cx));
-            const float w = __fmaf_rn(cx, cx, __fmaf_rn(cy, cy, __fmaf_rn(cz, cz, -fs.w)));
-            const float v = __fmaf_rn(b, b, -w);
-            // stage 1 (!(v < -theta)) and the "entirely behind the origin" cull of stage 2
-            if (!(v < ntheta) && !(b < nbcull)) mask |= 1u << u;
+        for (int u = 0; u < kScanGroup; u += 2) {
+            // past `cnt` the buffer holds stale spheres: the slow path below stops at cnt
+            const float4 s0 = tile[k0 + u], s1 = tile[k0 + u + 1];
+            const float cx0 = s0.x - f.ox, cy0 = s0.y - f.oy, cz0 = s0.z - f.oz;
+            const float cx1 = s1.x - f.ox, cy1 = s1.y - f.oy, cz1 = s1.z - f.oz;
+            const float b0 = __fmaf_rn(f.dz, cz0, __fmaf_rn(f.dy, cy0, f.dx * cx0));
+            const float b1 = __fmaf_rn(f.dz, cz1, __fmaf_rn(f.dy, cy1, f.dx * cx1));
+            const float w0 = __fmaf_rn(cx0, cx0, __fmaf_rn(cy0, cy0, __fmaf_rn(cz0, cz0, -s0.w)));
+            const float w1 = __fmaf_rn(cx1, cx1, __fmaf_rn(cy1, cy1, __fmaf_rn(cz1, cz1, -s1.w)));
+            const float v0 = __fmaf_rn(b0, b0, -w0), v1 = __fmaf_rn(b1, b1, -w1);
+            m = fmaxf(fmaxf(m, v0), v1);
         }
-        if (k0 + kScanGroup > cnt) mask &= (1u << (cnt - k0)) - 1u;
-        while (mask) {
-            const int u = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int k = k0 + u;
+        if (m < ntheta) continue;                        // no sphere of the group passes stage 1
+        const int kend = min(k0 + kScanGroup, cnt);
+#pragma unroll 1
+        for (int k = k0; k < kend; k++) {
             const float4 fs = tile[k];
             float b, v;
-            filter_stage1(f, fs, b, v);
+            if (!filter_stage1(f, fs, b, v)) continue;
             if (!filter_stage2(f, fs, b, v, cullk)) continue;
             const int sph = base + k;
             const int code = obj_code(OBJ_SPHERE, sph);
@@ -1383,7 +1414,7 @@ __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, con
                     best.t = t; best.order = ord; best.obj = code;
                     cullk = cullk_from(f, ray.inv_sqrt_a(), best);
                     if constexpr (ANY) {                  // a shadow ray only asks whether one exists
-                        if constexpr (COUNT) tl.filter += min(k0 + kScanGroup, cnt);
+                        if constexpr (COUNT) tl.filter += kend;
                         active = false;
                         return;
                     }
@@ -1538,7 +1569,7 @@ wf_scan_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fram
 
 // Folds the lights of every hit of one bounce (erl:209-252 in forward form, see pix_consume)
 // and emits the reflection rays of the next bounce.
-__global__ void __launch_bounds__(kWfThreads)
+__global__ void __launch_bounds__(kWfThreads, ERT_SHADE_MINBLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
          const __grid_constant__ WfBuf wf, int bounce)
 {
