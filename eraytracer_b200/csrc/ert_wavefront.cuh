@@ -1370,7 +1370,8 @@ __device__ __forceinline__ void scan_all_tiles(const DevScene &sc, ScanPipe &pp,
 #define ERT_SCAN_GROUP 16
 #endif
 constexpr int kScanGroup = ERT_SCAN_GROUP;
-static_assert(kScanGroup % 2 == 0 && kScanTile % kScanGroup == 0, "groups are whole pairs and tile whole groups");
+constexpr int kScanQuarters = 4, kScanQuarter = kScanGroup / kScanQuarters;
+static_assert(kScanGroup % 8 == 0 && kScanTile % kScanGroup == 0, "quarters are whole pairs, tiles whole groups");
 template <bool ANY, bool COUNT>
 __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, const RaySlot &ray, const float4 *tile,
                                           int cnt, int base, int skip_obj, int seed_obj, Hit &best, float &cullk,
@@ -1381,24 +1382,36 @@ __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, con
     const float m0 = (oabs + sc.abs_max < 1e17f) ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
 #pragma unroll 1
     for (int k0 = 0; k0 < cnt; k0 += kScanGroup) {
-        float m = m0;
+        // one running maximum per quarter of the group: the rare slow path then looks at 4 spheres, not 16
+        float mq[kScanQuarters];
 #pragma unroll
-        for (int u = 0; u < kScanGroup; u += 2) {
-            // past `cnt` the buffer holds stale spheres: the slow path below stops at cnt
-            const float4 s0 = tile[k0 + u], s1 = tile[k0 + u + 1];
-            const float cx0 = s0.x - f.ox, cy0 = s0.y - f.oy, cz0 = s0.z - f.oz;
-            const float cx1 = s1.x - f.ox, cy1 = s1.y - f.oy, cz1 = s1.z - f.oz;
-            const float b0 = __fmaf_rn(f.dz, cz0, __fmaf_rn(f.dy, cy0, f.dx * cx0));
-            const float b1 = __fmaf_rn(f.dz, cz1, __fmaf_rn(f.dy, cy1, f.dx * cx1));
-            const float w0 = __fmaf_rn(cx0, cx0, __fmaf_rn(cy0, cy0, __fmaf_rn(cz0, cz0, -s0.w)));
-            const float w1 = __fmaf_rn(cx1, cx1, __fmaf_rn(cy1, cy1, __fmaf_rn(cz1, cz1, -s1.w)));
-            const float v0 = __fmaf_rn(b0, b0, -w0), v1 = __fmaf_rn(b1, b1, -w1);
-            m = fmaxf(fmaxf(m, v0), v1);
+        for (int q = 0; q < kScanQuarters; q++) {
+            float m = m0;
+#pragma unroll
+            for (int u = q * kScanQuarter; u < (q + 1) * kScanQuarter; u += 2) {
+                // past `cnt` the buffer holds stale spheres: the slow path below stops at cnt
+                const float4 s0 = tile[k0 + u], s1 = tile[k0 + u + 1];
+                const float cx0 = s0.x - f.ox, cy0 = s0.y - f.oy, cz0 = s0.z - f.oz;
+                const float cx1 = s1.x - f.ox, cy1 = s1.y - f.oy, cz1 = s1.z - f.oz;
+                const float b0 = __fmaf_rn(f.dz, cz0, __fmaf_rn(f.dy, cy0, f.dx * cx0));
+                const float b1 = __fmaf_rn(f.dz, cz1, __fmaf_rn(f.dy, cy1, f.dx * cx1));
+                const float w0 = __fmaf_rn(cx0, cx0, __fmaf_rn(cy0, cy0, __fmaf_rn(cz0, cz0, -s0.w)));
+                const float w1 = __fmaf_rn(cx1, cx1, __fmaf_rn(cy1, cy1, __fmaf_rn(cz1, cz1, -s1.w)));
+                const float v0 = __fmaf_rn(b0, b0, -w0), v1 = __fmaf_rn(b1, b1, -w1);
+                m = fmaxf(fmaxf(m, v0), v1);
+            }
+            mq[q] = m;
         }
-        if (m < ntheta) continue;                        // no sphere of the group passes stage 1
-        const int kend = min(k0 + kScanGroup, cnt);
+        float mall = mq[0];
+#pragma unroll
+        for (int q = 1; q < kScanQuarters; q++) mall = fmaxf(mall, mq[q]);
+        if (mall < ntheta) continue;                     // no sphere of the group passes stage 1
+        unsigned int qmask = 0u;
+#pragma unroll
+        for (int q = 0; q < kScanQuarters; q++) qmask |= (mq[q] < ntheta) ? 0u : (1u << q);
 #pragma unroll 1
-        for (int k = k0; k < kend; k++) {
+        for (int k = k0; k < min(k0 + kScanGroup, cnt); k++) {
+            if (!((qmask >> ((k - k0) / kScanQuarter)) & 1u)) { k += kScanQuarter - 1; continue; }
             const float4 fs = tile[k];
             float b, v;
             if (!filter_stage1(f, fs, b, v)) continue;
@@ -1414,7 +1427,7 @@ __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, con
                     best.t = t; best.order = ord; best.obj = code;
                     cullk = cullk_from(f, ray.inv_sqrt_a(), best);
                     if constexpr (ANY) {                  // a shadow ray only asks whether one exists
-                        if constexpr (COUNT) tl.filter += kend;
+                        if constexpr (COUNT) tl.filter += min(k0 + kScanGroup, cnt);
                         active = false;
                         return;
                     }
