@@ -1,13 +1,16 @@
 #!/bin/bash
-# cell-grid A/B: parity tests, then C4 bench lines over library variants x grid densities
-mkdir -p gpurun_out; rm -f gpurun_out/h_*.json
+# A/B of library build variants: cell-grid parity tests, then bench lines (WORKLOAD, default c4) over
+# "variant:density[:ENV=VAL]" combos; variant = base or the suffix of eraytracer_b200/lib/libert_b200_<variant>.so
+mkdir -p gpurun_out; rm -f gpurun_out/h_*.json gpurun_out/h_*.err
 timeout 900 python -m pytest tests/test_gpu_cell_grid.py -x -q > gpurun_out/grid_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/grid_pytest.log
 tail -5 gpurun_out/grid_pytest.log
-B="python bench.py --workload c4 --steps 5 --warmup 2 --no-cpu-baseline --accel grid"
+W=${WORKLOAD:-c4}
+B="python bench.py --workload $W --steps 5 --warmup 2 --no-cpu-baseline --accel grid"
 for combo in "$@"; do
-  v=${combo%%:*}; d=${combo##*:}
+  IFS=: read v d e <<< "$combo"
   lib=$PWD/eraytracer_b200/lib/libert_b200.so; [ "$v" != base ] && lib=$PWD/eraytracer_b200/lib/libert_b200_$v.so
-  ERT_B200_LIB=$lib ERT_CELL_GRID_DENSITY=$d timeout 300 $B > gpurun_out/h_${v}_d$d.json 2> gpurun_out/h_${v}_d$d.err || tail -3 gpurun_out/h_${v}_d$d.err
+  tag=${v}_d${d}_${e//=/}
+  env ERT_B200_LIB=$lib ERT_CELL_GRID_DENSITY=$d ${e:-X=1} timeout 300 $B > gpurun_out/h_$tag.json 2> gpurun_out/h_$tag.err || tail -3 gpurun_out/h_$tag.err
 done
 python - <<PY
 import json,glob

@@ -1,0 +1,40 @@
+"""Times one row-band part of a frame on one GPU (what each GPU of an N-GPU run does).
+
+usage: python tools/part_probe.py [workload] [n_parts] [reps]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from eraytracer_b200 import _lib, multigpu, scene as sc  # noqa: E402
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "c4"
+    n_parts = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+    w, h, depth = 3840, 2160, 5
+    flat = sc.synthetic_scene(wl)
+    dev = flat.upload(0)
+    band = multigpu.default_band_rows(h, n_parts)
+    for flags, tag in ((0, "plain"), (_lib.FLAG_TIME_KERNELS, "timed")):
+        ms, split = [], None
+        for i in range(reps + 2):
+            _lib.l2_flush(0)
+            dev.render_async(w, h, depth, slot=0, fmt="rgb8", accel="auto", band_rows=band, n_parts=n_parts, part=0,
+                             flags=flags)
+            dev.wait(0)
+            st = dev.stats(0)
+            if i >= 2:
+                ms.append(st["kernel_ms"])
+                split = (st["path_ms"], st["shadow_ms"], st["other_ms"], st["gpu_launches"])
+        print("%s part 0 of %d (%s): kernel_ms median %.3f min %.3f; path/shadow/other %s rays %d"
+              % (wl, n_parts, tag, float(np.median(ms)), min(ms), split, st["rays"]))
+    dev.close()
+
+
+if __name__ == "__main__":
+    main()
