@@ -84,6 +84,20 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
         for (int a = 0; a < 3; a++) cell_grid_range(out, a, centers[k * 3 + a] - r, centers[k * 3 + a] + r, i0[a], i1[a]);
     };
     const size_t sx = 1, sy = (size_t)out.res[0], sz = (size_t)out.res[0] * (size_t)out.res[1];
+    // A cell inside the box of a sphere may still be out of the ball's reach (the corners of the box):
+    // the ball inflated by eps must come within the cell, also inflated by eps for the float planes.
+    auto reaches = [&](int64_t k, int x, int y, int z) {
+        const double r = std::fabs(radii[k]) + 2.0 * eps;
+        const int c[3] = {x, y, z};
+        double d2 = 0;
+        for (int a = 0; a < 3; a++) {
+            const double lo_a = (double)out.lo[a] + (double)c[a] * (double)out.cs, hi_a = lo_a + (double)out.cs;
+            const double p = centers[k * 3 + a];
+            const double d = p < lo_a ? lo_a - p : (p > hi_a ? p - hi_a : 0.0);
+            d2 += d * d;
+        }
+        return d2 <= r * r * (1.0 + 1e-9);
+    };
     for (int64_t k = 0; k < n; k++) {
         int i0[3], i1[3];
         range(k, i0, i1);
@@ -94,11 +108,11 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
             if ((int)out.big.size() > kCellGridMaxBig) { out = CellGrid(); return; }
             continue;
         }
-        refs += cells;
-        if (refs >= kCellGridMaxRefs) { out = CellGrid(); return; }
         for (int z = i0[2]; z <= i1[2]; z++)
             for (int y = i0[1]; y <= i1[1]; y++)
-                for (int x = i0[0]; x <= i1[0]; x++) count[x * sx + y * sy + z * sz]++;
+                for (int x = i0[0]; x <= i1[0]; x++)
+                    if (reaches(k, x, y, z)) { count[x * sx + y * sy + z * sz]++; refs++; }
+        if (refs >= kCellGridMaxRefs) { out = CellGrid(); return; }
     }
     // pass 2: offsets, packed cell words
     out.cells.resize(n_cells);
@@ -120,6 +134,7 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
         for (int z = i0[2]; z <= i1[2]; z++)
             for (int y = i0[1]; y <= i1[1]; y++)
                 for (int x = i0[0]; x <= i1[0]; x++) {
+                    if (!reaches(k, x, y, z)) continue;
                     uint32_t slot = cursor[x * sx + y * sy + z * sz]++;
                     memcpy(&out.ref_filter[(size_t)slot * 4], &filter[(size_t)k * 4], 16);
                     out.ref_sph[slot] = (int32_t)k;

@@ -16,7 +16,7 @@
 
 namespace ert {
 
-constexpr double kCellGridDensity = 0.5;     // default: cells per sphere (ERT_CELL_GRID_DENSITY)
+constexpr double kCellGridDensity = 0.35;    // default: cells per sphere (ERT_CELL_GRID_DENSITY)
 constexpr int kCellGridMinSpheres = 256;     // smaller scenes do not get one
 constexpr int kCellGridMaxRes = 1024;        // cells per axis (the walk keeps plane indices as floats)
 constexpr int kCellGridMaxCount = 127;       // spheres per cell (7 bits of the packed cell word)
