@@ -802,7 +802,8 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
         e++;
         float fb, fv;
         TALLY(filter);
-        if (filter_stage1(f, fs, fb, fv) && filter_stage2(f, fs, fb, fv, cull0) && obj_code(OBJ_SPHERE, sph) != target) {
+        // the target itself is the usual first candidate of a lit ray: it is recognised before the stage-2 cull
+        if (filter_stage1(f, fs, fb, fv) && obj_code(OBJ_SPHERE, sph) != target && filter_stage2(f, fs, fb, fv, cull0)) {
             double th;
             TALLY(exact_sph);
             if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
