@@ -306,6 +306,19 @@ def gpu_arm(args, rank, world, local_rank):
     dev.render_async(w, h, depth, slot=0, flags=_lib.FLAG_COUNT_TESTS, camera=camera_for(0), **common)
     dev.wait(0)
     counted = dev.stats(0)
+    # per-level ray counts of this rank's part (untimed): the reference re-traces the reflection once per
+    # light (erl:216-224), so level b of its recursion runs L^b times; frames that did not go through the
+    # wavefront are run through it once to get the counts
+    levels = counted
+    if not counted.get("bounces_recorded"):
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(0), **dict(common, accel="bvh"))
+        dev.wait(0)
+        levels = dev.stats(0)
+    n_l = int(len(flat.lights))
+    uniq = sum(p_ + n_l * h_ for p_, h_ in zip(levels["bounce_path_rays"], levels["bounce_hits"]))
+    refeq = sum((n_l ** b) * (p_ + n_l * h_)
+                for b, (p_, h_) in enumerate(zip(levels["bounce_path_rays"], levels["bounce_hits"])))
+    refeq_ratio = (refeq / uniq) if uniq else 1.0
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -432,6 +445,12 @@ def gpu_arm(args, rank, world, local_rank):
                             "ert_render() per step: camera + params in, kernel, pinned D2H of the RGB8 rows",
                     "frames_per_s": 1e3 / e2e_ms},
             "gpu_launches": launches_all,
+            "reference_equivalent": {
+                "ratio": refeq_ratio, "rays_per_frame": refeq_ratio * rays_all / steps,
+                "Mrays_per_s": refeq_ratio * value,
+                "what": "rays the reference would trace for the same frame: its lighting function re-traces the "
+                        "reflection once per light (erl:216-224), so level b runs L^b times; from the per-level "
+                        "counts of rank 0's part (ert_stats.bounce_path_rays / bounce_hits)"},
             "roofline": {
                 "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
                 "frac": achieved / peak, "traffic": traffic,

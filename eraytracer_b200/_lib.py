@@ -71,10 +71,16 @@ class Stats(ctypes.Structure):
                 ("shadow_box_tests", ctypes.c_uint64), ("shadow_filter_tests", ctypes.c_uint64),
                 ("path_ms", ctypes.c_double), ("shadow_ms", ctypes.c_double), ("other_ms", ctypes.c_double),
                 ("path_launches", ctypes.c_uint64), ("shadow_launches", ctypes.c_uint64),
-                ("cell_steps", ctypes.c_uint64), ("has_cell_grid", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
+                ("cell_steps", ctypes.c_uint64), ("has_cell_grid", ctypes.c_int32),
+                ("bounces_recorded", ctypes.c_int32),
+                ("bounce_path_rays", ctypes.c_uint64 * 16), ("bounce_hits", ctypes.c_uint64 * 16)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}
+        nb = d["bounces_recorded"]
+        d["bounce_path_rays"] = [int(v) for v in self.bounce_path_rays[:nb]]
+        d["bounce_hits"] = [int(v) for v in self.bounce_hits[:nb]]
+        return d
 
 
 # numpy views of the element records (same layout as the C structs)

@@ -84,6 +84,8 @@ struct Slot {
     unsigned int *wf_ctr = nullptr;
     int wf_ctr_depth = 0;
     unsigned int *wf_ctr_host = nullptr;           // pinned, for the early-out check of deep recursions
+    unsigned int *wf_ctr_all_host = nullptr;       // pinned, the counters of the first ERT_MAX_BOUNCE_STATS levels
+    int wf_levels = 0;                             // levels copied there by the last wavefront frame
     std::vector<cudaEvent_t> ticks;                // ERT_FLAG_TIME_KERNELS: one event before/after every launch
     std::vector<int> tick_class;                   // class of the launch between ticks[i] and ticks[i+1]
     unsigned long long *counters_dev = nullptr;
@@ -465,6 +467,7 @@ void destroy(ert_scene *s)
         if (sl.wf_mem) cudaFree(sl.wf_mem);
         if (sl.wf_ctr) cudaFree(sl.wf_ctr);
         if (sl.wf_ctr_host) cudaFreeHost(sl.wf_ctr_host);
+        if (sl.wf_ctr_all_host) cudaFreeHost(sl.wf_ctr_all_host);
         for (cudaEvent_t e : sl.ticks) cudaEventDestroy(e);
         if (sl.counters_dev) cudaFree(sl.counters_dev);
         if (sl.counters_host) cudaFreeHost(sl.counters_host);
@@ -593,6 +596,7 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
         sl.wf_ctr_depth = fp.depth;
     }
     if (!sl.wf_ctr_host) CU(cudaMallocHost(&sl.wf_ctr_host, kWfCtr * sizeof(unsigned int)));
+    if (!sl.wf_ctr_all_host) CU(cudaMallocHost(&sl.wf_ctr_all_host, ERT_MAX_BOUNCE_STATS * kWfCtr * sizeof(unsigned int)));
     unsigned char *base = (unsigned char *)sl.wf_mem;
     double *d = (double *)(base + o_dbl);
     int *i = (int *)(base + o_int);
@@ -719,6 +723,9 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     wf_finalize<<<s->wf_grid[3], kWfThreads, 0, st>>>(fp, wf);
     n++;
     TICK(2);
+    sl.wf_levels = std::min(fp.depth, (int)ERT_MAX_BOUNCE_STATS);
+    CU(cudaMemcpyAsync(sl.wf_ctr_all_host, wf.ctr, (size_t)sl.wf_levels * kWfCtr * sizeof(unsigned int),
+                       cudaMemcpyDeviceToHost, st));
     CU(cudaGetLastError());
 #undef WF_CHECK
 #undef TICK
@@ -744,6 +751,13 @@ int finish_slot(ert_scene *s, Slot &sl)
     sl.stats.exact_sphere_tests = c0[CNT_EXACT_SPH] + c1[CNT_EXACT_SPH];
     sl.stats.exact_other_tests = c0[CNT_EXACT_OTHER] + c1[CNT_EXACT_OTHER];
     sl.stats.cell_steps = c0[CNT_CELL] + c1[CNT_CELL];
+    sl.stats.bounces_recorded = sl.wf_levels;
+    for (int b = 0; b < sl.wf_levels; b++) {
+        const unsigned int *c = sl.wf_ctr_all_host + (size_t)b * kWfCtr;
+        sl.stats.bounce_hits[b] = c[WF_NHITS];
+        sl.stats.bounce_path_rays[b] = b == 0 ? sl.stats.pixels : sl.wf_ctr_all_host[(size_t)(b - 1) * kWfCtr + WF_NNEXT];
+    }
+    sl.wf_levels = 0;
     sl.stats.has_cell_grid = s->host.cgrid.enabled ? 1 : 0;
     sl.stats.path_box_tests = c0[CNT_BOX]; sl.stats.path_filter_tests = c0[CNT_FILTER];
     sl.stats.shadow_box_tests = c1[CNT_BOX]; sl.stats.shadow_filter_tests = c1[CNT_FILTER];

@@ -147,6 +147,8 @@ typedef struct ert_render_params {
     const ert_camera *camera;   /* NULL => the camera stored with the scene */
 } ert_render_params;
 
+#define ERT_MAX_BOUNCE_STATS 16
+
 typedef struct ert_stats {
     double kernel_ms;           /* CUDA-event time of the render kernel(s) on the slot's stream */
     double total_ms;            /* kernel(s) + device-to-host copies, CUDA events */
@@ -171,7 +173,12 @@ typedef struct ert_stats {
     /* ABI 3 */
     uint64_t cell_steps;            /* cells visited by the grid walks of path rays (ERT_FLAG_COUNT_TESTS) */
     int32_t has_cell_grid;          /* the scene has a cell grid (ERT_ACCEL_GRID is available) */
-    int32_t reserved2;
+    int32_t bounces_recorded;       /* entries of the two arrays below that are filled (wavefront frames only) */
+    /* Per reflection level b (0 = primary): path rays traced and hits found.  rays = sum_b (path[b] + L*hits[b]);
+     * the reference re-traces the reflection once per light (erl:216-224), so its own ray count for the
+     * same frame is sum_b L^b * (path[b] + L*hits[b]). */
+    uint64_t bounce_path_rays[ERT_MAX_BOUNCE_STATS];
+    uint64_t bounce_hits[ERT_MAX_BOUNCE_STATS];
 } ert_stats;
 
 typedef struct ert_scene ert_scene;     /* opaque: device-resident flattened scene */

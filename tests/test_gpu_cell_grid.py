@@ -215,3 +215,24 @@ def test_c4_full_4k_grid_equals_bvh(gpu):
     ol, tl = dev.trace_rays(rays, accel="linear")
     assert np.array_equal(og, ol) and np.array_equal(tg, tl)
     dev.close()
+
+
+def test_per_level_counts_and_the_reference_ray_count(c3):
+    """ert_stats.bounce_*: rays = sum_b (path[b] + L*hits[b]); the reference's own count for the frame
+    (reflection re-traced once per light, erl:216-224) = sum_b L^b * (path[b] + L*hits[b]) — checked
+    against the oracle in its literal re-tracing mode."""
+    flat, dev = c3
+    w, h, depth = 48, 27, 4
+    for accel in ("grid", "bvh"):
+        frame, st = dev.render(w, h, depth, fmt="f64", accel=accel)
+        L = len(flat.lights)
+        assert st["bounces_recorded"] == depth and st["bounce_path_rays"][0] == w * h
+        assert st["rays"] == sum(p + L * q for p, q in zip(st["bounce_path_rays"], st["bounce_hits"]))
+        cam, kind, f = oracle_scene_from_flat(flat)
+        ref, ref_rays, _ = orc.render(cam, kind, f, w, h, depth, retrace=True)
+        assert ref_rays == sum((L ** b) * (p + L * q)
+                               for b, (p, q) in enumerate(zip(st["bounce_path_rays"], st["bounce_hits"])))
+        assert np.array_equal(quantise(frame), quantise(ref.reshape(h, w, 3)))
+    # frames that do not go through the wavefront record no levels
+    _, st = dev.render(w, h, depth, fmt="f64", accel="exact")
+    assert st["bounces_recorded"] == 0 and st["bounce_hits"] == []
