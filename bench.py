@@ -36,6 +36,7 @@ WORKLOADS = {
     "c2d5": ("C2 demo scene 1920x1080 depth 5 (raytrace/1 default depth)", "demo", 1920, 1080, 5),
     "c3": ("C3 synthetic 10k-sphere scene 3840x2160, 3 point lights, depth 5", "c3", 3840, 2160, 5),
     "c4": ("C4 synthetic 1M-sphere scene 3840x2160, 3 point lights, depth 5 (accelerated nearest hit == linear scan)", "c4", 3840, 2160, 5),
+    "c4d1": ("C4 synthetic 1M-sphere scene 3840x2160, 3 point lights, depth 1 (run-concurrent.sh depth)", "c4", 3840, 2160, 1),
     "c5": ("C5 demo scene 7680x4320 depth 1, camera pose k of 64 per step", "demo", 7680, 4320, 1),
 }
 

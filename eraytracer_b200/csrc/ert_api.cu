@@ -450,7 +450,7 @@ int upload_scene(ert_scene *s)
         CU(cudaFuncSetAttribute(wf_scan_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
         CU(cudaFuncSetAttribute(wf_scan_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
         CU(cudaFuncSetAttribute(wf_scan_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_scan_path<false, false>, kWfThreads, kScanSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_scan_path<false, false>, kScanThreads, kScanSmem));
         s->wf_grid_scan = prop.multiProcessorCount * std::max(nb, 1);
     }
     return ERT_OK;
@@ -673,8 +673,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
         const bool sort = b >= 1 && !no_sort && !scan;
-        if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
-        else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fp, wf, b);
+        if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
+        else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
         else if (cells && b >= cells_from) {
             // path rays step through the cell grid (ERT_ACCEL_GRID)
             if (b == 0) wf_trace_path<true, COUNT, true, true><<<s->wf_grid[4], kWfThreads, 0, st>>>(d, fp, wf, b);
@@ -710,7 +710,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         n++;
         TICK(2);
         WF_CHECK("wf_emit_hits / wf_bin_*");
-        if (scan) wf_scan_shadow<COUNT><<<s->wf_grid_scan, kWfThreads, kScanSmem, st>>>(d, fps, wf, b);
+        if (scan) wf_scan_shadow<COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fps, wf, b);
         else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         TICK(1);

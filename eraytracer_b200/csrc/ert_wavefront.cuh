@@ -1318,6 +1318,11 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
 #ifndef ERT_SCAN_MINBLOCKS
 #define ERT_SCAN_MINBLOCKS 2
 #endif
+#ifndef ERT_SCAN_THREADS
+#define ERT_SCAN_THREADS 256
+#endif
+constexpr int kScanThreads = ERT_SCAN_THREADS;            // rays per block of the scan kernels (<= kWfThreads)
+static_assert(kScanThreads <= kWfThreads && kScanThreads % 32 == 0, "the ray slots are laid out for kWfThreads");
 constexpr int kScanTile = ERT_SCAN_TILE;                  // filter spheres per buffer (16 B each)
 static_assert(kScanTile % 8 == 0, "tiles are whole groups");
 constexpr int kScanSmem = 2 * kScanTile * 16;             // dynamic shared memory of the scan kernels
@@ -1441,7 +1446,7 @@ __device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, con
 }
 
 template <bool FIRST, bool COUNT>
-__global__ void __launch_bounds__(kWfThreads, ERT_SCAN_MINBLOCKS)
+__global__ void __launch_bounds__(kScanThreads, ERT_SCAN_MINBLOCKS)
 wf_scan_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
              const __grid_constant__ WfBuf wf, int bounce)
 {
@@ -1468,7 +1473,7 @@ wf_scan_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
     Tally<COUNT> tl;
     unsigned int rays = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kWfThreads);
+        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kScanThreads);
         __syncthreads();
         const unsigned long long base = s_base;
         if (base >= n) break;
@@ -1506,7 +1511,7 @@ wf_scan_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kWfThreads, ERT_SCAN_MINBLOCKS)
+__global__ void __launch_bounds__(kScanThreads, ERT_SCAN_MINBLOCKS)
 wf_scan_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                const __grid_constant__ WfBuf wf, int bounce)
 {
@@ -1534,7 +1539,7 @@ wf_scan_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fram
     Tally<COUNT> tl;
     unsigned int rays = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kWfThreads);
+        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kScanThreads);
         __syncthreads();
         const unsigned long long base = s_base;
         if (base >= total) break;
