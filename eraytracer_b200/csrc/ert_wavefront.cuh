@@ -1311,15 +1311,18 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
 // global -> shared by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) into a double buffer
 // that a block of 256 rays shares.  This is the kernel the FP32-issue roofline is about: 10
 // FP32-pipe instructions + 1 compare + 1/UNROLL of a broadcast LDS.128 per (ray, sphere).
-// A block takes 256 consecutive queue entries at a time (one ray per thread).
+// A block takes kScanThreads consecutive queue entries at a time (one ray per thread).  128 rays on
+// tiles of 1024 spheres, six blocks per SM, beat 256 rays on tiles of 2048, two blocks: the barrier
+// per tile then holds four warps instead of eight and 24 warps per SM hide the LDS latency
+// (wf_scan_path 59 -> 61 % of the FP32 issue peak on C3).
 #ifndef ERT_SCAN_TILE
-#define ERT_SCAN_TILE 2048
+#define ERT_SCAN_TILE 1024
 #endif
 #ifndef ERT_SCAN_MINBLOCKS
-#define ERT_SCAN_MINBLOCKS 2
+#define ERT_SCAN_MINBLOCKS 6
 #endif
 #ifndef ERT_SCAN_THREADS
-#define ERT_SCAN_THREADS 256
+#define ERT_SCAN_THREADS 128
 #endif
 constexpr int kScanThreads = ERT_SCAN_THREADS;            // rays per block of the scan kernels (<= kWfThreads)
 static_assert(kScanThreads <= kWfThreads && kScanThreads % 32 == 0, "the ray slots are laid out for kWfThreads");
