@@ -176,7 +176,8 @@ typedef struct ert_stats {
     int32_t bounces_recorded;       /* entries of the two arrays below that are filled (wavefront frames only) */
     /* Per reflection level b (0 = primary): path rays traced and hits found.  rays = sum_b (path[b] + L*hits[b]);
      * the reference re-traces the reflection once per light (erl:216-224), so its own ray count for the
-     * same frame is sum_b L^b * (path[b] + L*hits[b]). */
+     * same frame is sum_b L^b * (path[b] + L*hits[b]) (plus the reflections off surfaces of reflectivity
+     * exactly 0, which it traces and multiplies by 0, and this library does not trace). */
     uint64_t bounce_path_rays[ERT_MAX_BOUNCE_STATS];
     uint64_t bounce_hits[ERT_MAX_BOUNCE_STATS];
 } ert_stats;
