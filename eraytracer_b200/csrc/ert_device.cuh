@@ -550,6 +550,25 @@ __device__ __forceinline__ d3 hit_normal(const DevScene &sc, int obj, d3 P)
     }
 }
 
+// math:pow(Base, Power) of specular_term (erl:293).  Base is max(0, .) <= 1 + rounding.  Specular
+// powers are small whole numbers in every scene of the reference (618-665) and the benchmarks; for
+// those, square-and-multiply (<= 11 DMULs, each correctly rounded: a few ulp from the exact power,
+// like CUDA's pow, which is 2 ulp from glibc's) replaces the ~150-instruction general routine.
+__device__ __forceinline__ double spec_pow(double base, double power)
+{
+    if (power >= 0.0 && power <= 64.0 && power == floor(power)) {
+        unsigned int n = (unsigned int)power;
+        double r = 1.0, b = base;
+        while (n) {
+            if (n & 1u) r *= b;
+            b *= b;
+            n >>= 1;
+        }
+        return r;
+    }
+    return pow(base, power);
+}
+
 // LightColour (*) (Diffuse + Specular) of one unshadowed light (erl:225-247, 272-297);
 // D is the direction of the ray that hit.
 __device__ __forceinline__ d3 light_term(const double *l, const double *mat, d3 P, d3 N, d3 D)
@@ -560,7 +579,7 @@ __device__ __forceinline__ d3 light_term(const double *l, const double *mat, d3 
     d3 diffuse = vscale(mk(mat[0], mat[1], mat[2]), max0(vdot(N, ldir)));
     // specular_term erl:285-297
     double base = max0(vdot(vnormalize(vadd(ldir, vneg(D))), N));
-    d3 specular = vscale(mk(l[6], l[7], l[8]), mat[4] * pow(base, mat[3]));
+    d3 specular = vscale(mk(l[6], l[7], l[8]), mat[4] * spec_pow(base, mat[3]));
     d3 contribution = vadd(diffuse, specular);                       // erl:225-238
     return vscale(vcmul(mk(l[0], l[1], l[2]), contribution), 1.0);   // erl:243-247, shadow = 1
 }
