@@ -229,3 +229,23 @@ def test_pose_camera():
     c0, c16 = sc.pose_camera(0), sc.pose_camera(16)
     assert list(c0.location) == [0.0, -0.5, -2.0]
     assert abs(c16.location[0] - 4.0) < 1e-12 and abs(c16.location[2] + 3.0) < 1e-12
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The driver's contract for `bench.py --impl reference`: exactly one JSON line on stdout
+    (whatever libraries print goes to stderr), same metric and config keys as the GPU arm."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mrays/s" and d["unit"] == "Mrays/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
