@@ -336,6 +336,7 @@ template <class R>
 __device__ __forceinline__ bool filter_stage2(const R &f, float4 s, float b, float v, float cull)
 {
     if (b < -f.bcull) return false;
+    if (cull == __int_as_float(0x7f800000)) return true;      // no incumbent yet: nothing is "beyond" it
     float arg = fmaxf(v, 0.f) + ERT_REL17 * (b * b + s.w) + f.pad2;
     float s_lo = b - fabsf(b) * ERT_REL16 - sqrtf(arg) * 1.000001f - f.bcull;
     return !(s_lo > cull);
