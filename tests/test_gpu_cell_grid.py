@@ -305,3 +305,17 @@ def test_grid_path_edge_scenes_match_the_oracle(gpu, case):
         # the oracle still trace that reflection, so only the "deep" case may count fewer rays
         assert st["rays"] == ref_rays or (case == "deep" and st["rays"] < ref_rays), (case, accel)
     dev.close()
+
+
+def test_committed_synthetic_golden_fixture(gpu):
+    """Every strategy against tests/golden/synthetic_images.json (no oracle build needed)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "synthetic_images.json")))
+    for key, img in g["images"].items():
+        dev = sc.synthetic_scene("c3", n_spheres=img["n_spheres"]).upload(0)
+        for accel in ("auto", "grid", "bvh", "linear", "bvh_mega", "exact"):
+            rgb8, st = dev.render(img["width"], img["height"], img["depth"], fmt="rgb8", accel=accel)
+            assert rgb8.reshape(-1).tolist() == img["rgb8"], (key, accel)
+            assert st["rays"] == img["rays"], (key, accel)
+        dev.close()

@@ -156,3 +156,21 @@ def test_synthetic_scene_oracle_small_vs_python():
     py = np.array([p[1] for p in po.raytraced_pixel_list_simple(24, 14, scene, 3)]).reshape(14, 24, 3)
     assert np.array_equal(ref, py)
     assert ref.any()
+
+
+SYNTHETIC = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "synthetic_images.json")))
+
+
+@pytest.mark.parametrize("key", sorted(SYNTHETIC["images"]))
+def test_synthetic_golden_fixture_is_reproduced(key):
+    """tests/golden/synthetic_images.json (random-sphere scenes, made by make_golden_synthetic.py, which
+    also checks a lattice of pixels against the pure-Python restatement bit for bit)."""
+    from eraytracer_b200 import scene as sc
+    from helpers import oracle_scene_from_flat
+    g = SYNTHETIC["images"][key]
+    flat = sc.synthetic_scene("c3", n_spheres=g["n_spheres"])
+    cam, kind, f = oracle_scene_from_flat(flat)
+    rgb, rays, tests = orc.render(cam, kind, f, g["width"], g["height"], g["depth"])
+    assert orc.quantise_image(rgb).reshape(-1).tolist() == g["rgb8"]
+    assert hashlib.sha256(np.ascontiguousarray(rgb).tobytes()).hexdigest() == g["f64_sha256"]
+    assert rays == g["rays"] and tests == g["tests"]
