@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -250,13 +251,22 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         }
         radii[(size_t)k] = s.radius;
     }
+    std::thread bvh_thread, cell_thread;
+    struct Joiner {                              // joins on every way out of this function
+        std::thread &a, &b;
+        ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
+    } joiner{bvh_thread, cell_thread};
     {
         // tuning knobs of the BVH builder (defaults are the measured best, DESIGN.md "BVH")
         int leaf_max = kBvhLeafMax;
         float trav_cost = kBvhTravCost;
         if (const char *e = getenv("ERT_BVH_LEAF_MAX")) leaf_max = atoi(e);
         if (const char *e = getenv("ERT_BVH_TRAV_COST")) trav_cost = (float)atof(e);
-        build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
+        // the three builders (BVH, cell grid, direction grids) are independent: the BVH and the cell grid
+        // are built on their own threads while this one goes on to the direction grids
+        bvh_thread = std::thread([&h, &centers, &radii, leaf_max, trav_cost] {
+            build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
+        });
     }
     if (h.n_spheres > 0) {
         double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
@@ -273,6 +283,16 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         }
     }
     {
+        // cell grid for the path rays; ERT_CELL_GRID=0 turns it off, ERT_CELL_GRID_DENSITY = cells per sphere
+        double density = kCellGridDensity;
+        if (const char *e = getenv("ERT_CELL_GRID_DENSITY")) density = atof(e);
+        const char *off = getenv("ERT_CELL_GRID");
+        if (!(off && atoi(off) == 0))
+            cell_thread = std::thread([&h, &centers, &radii, density] {
+                build_cell_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, h.abs_max, density, h.cgrid);
+            });
+    }
+    {
         // direction grids for shadow rays: worth their memory once a walk through the BVH costs more
         // than a handful of candidate tests; ERT_LIGHT_GRID_RES=0 turns them off
         int res = kLightGridRes;
@@ -284,14 +304,8 @@ int flatten(const ert_scene_desc *d, HostScene &h)
             build_light_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, &h.lights[(size_t)g * 9 + 3],
                              res, h.lgrids[(size_t)g]);
     }
-    {
-        // cell grid for the path rays; ERT_CELL_GRID=0 turns it off, ERT_CELL_GRID_DENSITY = cells per sphere
-        double density = kCellGridDensity;
-        if (const char *e = getenv("ERT_CELL_GRID_DENSITY")) density = atof(e);
-        const char *off = getenv("ERT_CELL_GRID");
-        if (!(off && atoi(off) == 0))
-            build_cell_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, h.abs_max, density, h.cgrid);
-    }
+    if (bvh_thread.joinable()) bvh_thread.join();
+    if (cell_thread.joinable()) cell_thread.join();
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
