@@ -1,0 +1,160 @@
+// Prototype (NOT part of the library): an FP32 "certain hit" bound for filter survivors.
+//
+// Today a sphere that passes the FP32 filter goes straight to the literal FP64 test, because only
+// that test yields the distance that lets the walk stop (DESIGN.md "(f) Next", item 1).  If the
+// filter could also say "this IS a hit, and it is no farther than s_up", a walk could take s_up as
+// its cull distance at once and leave the FP64 test for later, a warp at a time.  Stage 2 of the
+// filter already bounds the near root from below with error terms derived for exactly these
+// quantities; this probe checks the mirror image on the host with the device's FP32 operations:
+//
+//     argL   = v - 2^-17 (b^2 + R) - pad2                    lower bound of the normalised discriminant
+//     s_lo   = b - |b| 2^-16 - sqrt(max(v,0) + 2^-17 (b^2+R) + pad2) * 1.000001 - bcull   (stage 2)
+//     certain = argL > thr(a)  and  s_lo > 0
+//     s_up   = b + |b| 2^-16 - sqrt(argL) * 0.999999 + bcull
+//
+// against the literal double test (erl:364-397): whenever `certain`, the reference must hit and its
+// geometric distance t/sqrt(a) must be <= s_up (1 + 2^-16) + m4.
+//
+//     g++ -O2 -std=c++17 -ffp-contract=off -o /tmp/certain_hit_probe tools/certain_hit_probe.cpp
+//     /tmp/certain_hit_probe        adversarial mix: 10 M pairs, 0 violations, 58 % of the hits certain
+//     /tmp/certain_hit_probe c4     the benchmark regime (r 0.2..1, coordinates to 300): see DESIGN.md
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <random>
+#include <string>
+
+namespace {
+constexpr float kU = 5.9604644775390625e-8f, kRel16 = 1.52587890625e-5f, kRel17 = 7.62939453125e-6f;
+constexpr double kKD = 1.0000019073486328125;
+float f_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, INFINITY); return f; }
+
+struct FS { float c[3], R, pad_c, eta_c; };
+FS make_filter_sphere(const double *c, double r)           // ert_api.cu: make_filter_sphere
+{
+    FS o;
+    const double u = 5.9604644775390625e-8;
+    double eta = 0;
+    for (int a = 0; a < 3; a++) { o.c[a] = (float)c[a]; eta = std::fmax(eta, std::fabs(c[a] - (double)o.c[a])); }
+    eta *= 2.0;
+    r = std::fabs(r);
+    double pad = 16.0 * r * eta + 4.0 * eta * eta / u;
+    double R = r * r * (1.0 + 3.814697265625e-6) + pad;
+    o.R = std::nextafterf(f_up(R), INFINITY);
+    o.pad_c = f_up(pad);
+    o.eta_c = f_up(eta);
+    return o;
+}
+struct Ray { float o[3], d[3], theta, bcull, pad2, m4; double a, inv; };
+Ray make_sray(const double *O, const double *D, float r_max, float eta_c_max, float pad_c_max, float abs_max)
+{
+    Ray f;
+    f.a = D[0] * D[0] + D[1] * D[1] + D[2] * D[2];
+    f.inv = (std::fabs(f.a - 1.0) <= 1e-9) ? (1.5 - 0.5 * f.a) : 1.0 / std::sqrt(f.a);
+    const double k = f.inv * kKD;
+    float eo = 0, oabs = 0;
+    for (int x = 0; x < 3; x++) {
+        f.o[x] = (float)O[x];
+        f.d[x] = (float)(D[x] * k);
+        eo = std::fmax(eo, std::fabs((float)(O[x] - (double)f.o[x])));
+        oabs = std::fmax(oabs, std::fabs(f.o[x]));
+    }
+    eo = 2.0f * eo * 1.0001f;
+    f.theta = 16.0f * r_max * eo + 8.0f * eo * (eo / kU);
+    f.bcull = 2.0f * (5.0f * kU * r_max + 2.0f * eo + 2.0f * eta_c_max);
+    f.pad2 = 2.0f * (f.theta + pad_c_max) + 1e-30f;
+    f.m4 = 4.0f * (eo + 32.0f * kU * (oabs + abs_max));
+    return f;
+}
+bool sphere_exact(const double *O, const double *D, double a, const double *c, double r, double &t)
+{
+    double ox = O[0] - c[0], oy = O[1] - c[1], oz = O[2] - c[2];
+    double b = 2.0 * (D[0] * ox + D[1] * oy + D[2] * oz);
+    double cc = ox * ox + oy * oy + oz * oz - r * r;
+    double disc = b * b - 4.0 * a * cc;
+    if (disc >= 0.001) {
+        double sq = std::sqrt(disc);
+        double t0 = (-b + sq) / 2.0, t1 = (-b - sq) / 2.0;
+        if (t0 >= 0.0 && t1 >= 0.0) { t = t0 < t1 ? t0 : t1; return true; }
+    }
+    return false;
+}
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    const bool c4 = argc > 1 && std::string(argv[1]) == "c4";   // the regime of the benchmark scenes instead of the adversarial mix
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    std::normal_distribution<double> N(0.0, 1.0);
+    uint64_t samples = 0, hits = 0, certain = 0, bad_miss = 0, bad_dist = 0, filter_drop = 0;
+    double worst = 0;
+    for (int scene = 0; scene < 4000; scene++) {
+        double scale = std::pow(10.0, U(rng) * 4 - 1);                // scene extent 0.1 .. 1000
+        double offset = (U(rng) < 0.5) ? 0.0 : std::pow(10.0, U(rng) * 4) * (U(rng) < 0.5 ? -1 : 1);
+        const bool f32 = U(rng) < 0.5;
+        double rlo = scale * std::pow(10.0, -2 - U(rng)), rhi = rlo * (1 + 20 * U(rng));
+        if (c4) { scale = 200.0; offset = 100.0; rlo = 0.2; rhi = 1.0; }
+        const float r_max = f_up(rhi), abs_max = f_up(std::fabs(offset) + 2 * scale + rhi);
+        // scene-wide pads: take them from a sample of spheres like the real flattening does
+        float eta_c_max = 0, pad_c_max = 0;
+        double cs[64][3], rs[64];
+        FS fs[64];
+        for (int s = 0; s < 64; s++) {
+            for (int a = 0; a < 3; a++) { cs[s][a] = offset + scale * (2 * U(rng) - 1); if (f32) cs[s][a] = (double)(float)cs[s][a]; }
+            rs[s] = rlo + (rhi - rlo) * U(rng);
+            if (f32) rs[s] = (double)(float)rs[s];
+            fs[s] = make_filter_sphere(cs[s], rs[s]);
+            eta_c_max = std::fmax(eta_c_max, fs[s].eta_c);
+            pad_c_max = std::fmax(pad_c_max, fs[s].pad_c);
+        }
+        for (int k = 0; k < 2500; k++) {
+            const int s = (int)(U(rng) * 64) & 63;
+            // a ray aimed near sphere s: impact parameter 0 .. 1.3 r, origin 1.0001 r .. 1000 r away (or inside)
+            double dir[3] = {N(rng), N(rng), N(rng)};
+            double n = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+            for (double &x : dir) x /= n;
+            double perp[3] = {N(rng), N(rng), N(rng)};
+            double dp = perp[0] * dir[0] + perp[1] * dir[1] + perp[2] * dir[2];
+            for (int a = 0; a < 3; a++) perp[a] -= dp * dir[a];
+            n = std::sqrt(perp[0] * perp[0] + perp[1] * perp[1] + perp[2] * perp[2]);
+            double edge = (U(rng) < 0.3) ? 1.0 - std::pow(10.0, -1 - 12 * U(rng)) * (U(rng) < 0.5 ? 1 : -1) : 1.3 * U(rng);
+            if (c4) edge = 1.3 * std::sqrt(U(rng));                     // uniform over the disc of impact parameters
+            double dist = rs[s] * ((U(rng) < 0.1) ? U(rng) : 1.0001 + std::pow(10.0, 3 * U(rng)));
+            if (c4) dist = rs[s] * 1.0001 + 60.0 * U(rng);
+            double O[3], D[3];
+            const double len = (c4 || U(rng) < 0.7) ? 1.0 : std::pow(10.0, 2 * U(rng) - 1);   // non-unit directions too
+            for (int a = 0; a < 3; a++) {
+                O[a] = cs[s][a] - dir[a] * dist + perp[a] / n * rs[s] * edge;
+                D[a] = dir[a] * len;
+            }
+            Ray f = make_sray(O, D, r_max, eta_c_max, pad_c_max, abs_max);
+            // stage 1
+            const float cx = fs[s].c[0] - f.o[0], cy = fs[s].c[1] - f.o[1], cz = fs[s].c[2] - f.o[2];
+            const float b = std::fmaf(f.d[2], cz, std::fmaf(f.d[1], cy, f.d[0] * cx));
+            const float w = std::fmaf(cx, cx, std::fmaf(cy, cy, std::fmaf(cz, cz, -fs[s].R)));
+            const float v = std::fmaf(b, b, -w);
+            double t = 0;
+            const bool hit = sphere_exact(O, D, f.a, cs[s], rs[s], t);
+            samples++;
+            hits += hit;
+            if (v < -f.theta || b < -f.bcull) { if (hit) filter_drop++; continue; }
+            const float err = kRel17 * (b * b + fs[s].R) + f.pad2;
+            const float argL = v - err;
+            const float s_lo = b - std::fabs(b) * kRel16 - std::sqrt(std::fmax(v, 0.f) + err) * 1.000001f - f.bcull;
+            const float thr = 0.001f * std::fmax(1.0f, (float)(1.0 / f.a));
+            if (!(argL > thr && s_lo > 0.f)) continue;
+            certain++;
+            if (!hit) { bad_miss++; continue; }
+            const float s_up = b + std::fabs(b) * kRel16 - std::sqrt(argL) * 0.999999f + f.bcull;
+            const double geo = t * f.inv;
+            const double bound = (double)s_up * (1.0 + (double)kRel16) + (double)f.m4;
+            if (geo > bound) { bad_dist++; worst = std::fmax(worst, geo - bound); }
+        }
+    }
+    printf("samples %llu  reference hits %llu  certain %llu (%.1f %% of the hits)\n", (unsigned long long)samples,
+           (unsigned long long)hits, (unsigned long long)certain, 100.0 * (double)certain / (double)hits);
+    printf("filter dropped a hit: %llu   certain but the reference misses: %llu   distance above the bound: %llu (worst %.3g)\n",
+           (unsigned long long)filter_drop, (unsigned long long)bad_miss, (unsigned long long)bad_dist, worst);
+    return (filter_drop || bad_miss || bad_dist) ? 1 : 0;
+}
