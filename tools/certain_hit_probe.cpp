@@ -1,7 +1,9 @@
 // Prototype (NOT part of the library): an FP32 "certain hit" bound for filter survivors.
 //
-// Today a sphere that passes the FP32 filter goes straight to the literal FP64 test, because only
-// that test yields the distance that lets the walk stop (DESIGN.md "(f) Next", item 1).  If the
+// A sphere that passes the FP32 filter goes straight to the literal FP64 test, because only that
+// test yields the distance that lets the walk stop.  (The kernel built on the bound below — hits
+// parked and tested a warp at a time — was bit-identical but 7 % slower on the path walks: DESIGN.md
+// "Measured and dropped".  The probe stays as the record of the bound.)  If the
 // filter could also say "this IS a hit, and it is no farther than s_up", a walk could take s_up as
 // its cull distance at once and leave the FP64 test for later, a warp at a time.  Stage 2 of the
 // filter already bounds the near root from below with error terms derived for exactly these
