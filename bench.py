@@ -381,6 +381,50 @@ def gpu_arm(args, rank, world, local_rank):
             e2e_dev_ms += st["total_ms"]
             d2h += st["d2h_bytes"]
     barrier()
+    # ---- the FP32-roofline kernel on this scene: the brute-force scan (the reference's linear scan,
+    # erl:300-346) over a 4-row band of the same frame, every ray against every sphere ----
+    scan = None
+    if rank == 0 and len(flat.spheres) > 192 and not args.no_scan_roofline:
+        band = dict(fmt=fmt, accel="linear", band_rows=4, n_parts=max(h // 4, 1), part=max(h // 8, 0))
+        for _ in range(2):
+            dev.render_async(w, h, depth, slot=0, camera=camera_for(0), **band)
+            dev.wait(0)
+        dev.render_async(w, h, depth, slot=0, flags=_lib.FLAG_COUNT_TESTS, camera=camera_for(0), **band)
+        dev.wait(0)
+        sc_counted = dev.stats(0)
+        sc_split = {"path_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "path_launches": 0, "shadow_launches": 0}
+        sc_ms, sc_steps = 0.0, 3
+        for _ in range(sc_steps):
+            _lib.l2_flush(local_rank)
+            dev.render_async(w, h, depth, slot=0, flags=_lib.FLAG_TIME_KERNELS, camera=camera_for(0), **band)
+            dev.wait(0)
+            st = dev.stats(0)
+            sc_ms += st["kernel_ms"]
+            for k in sc_split:
+                sc_split[k] += st[k]
+        p_s = sc_split["path_ms"] / sc_steps * 1e-3
+        s_s = sc_split["shadow_ms"] / sc_steps * 1e-3
+        scan = {
+            "kernel": "wf_scan<path> (ert_scan.cuh): FP32 filter of every (path ray, sphere) pair, packed FFMA2, "
+                      "TMA-fed shared-memory ring",
+            "workload": "rows %d-%d of the %dx%d frame, depth %d, accel=linear: %d rays x %d spheres" % (
+                4 * band["part"], 4 * band["part"] + 3, w, h, depth, sc_counted["rays"], len(flat.spheres)),
+            "bound": "fp32", "unit": "Glane-instr/s", "peak": peak / 1e9,
+            "accounting": "10 FP32-pipe lane-instructions per (ray, sphere) filter test (3 FADD, 1 FMUL, 6 FFMA), "
+                          "tests counted by an instrumented run of the same band, divided by the CUDA-event time of "
+                          "the scan launches of that class inside %d timed frames" % sc_steps,
+            "path_filter_tests": int(sc_counted["path_filter_tests"]),
+            "shadow_filter_tests": int(sc_counted["shadow_filter_tests"]),
+            "exact_fp64_sphere_tests": int(sc_counted["exact_sphere_tests"]),
+            "path_ms": p_s * 1e3, "shadow_ms": s_s * 1e3, "frame_ms": sc_ms / sc_steps,
+            "path_launches": sc_split["path_launches"] / sc_steps,
+            "achieved": sc_counted["path_filter_tests"] * 10 / max(p_s, 1e-12) / 1e9,
+            "frac": sc_counted["path_filter_tests"] * 10 / max(p_s, 1e-12) / peak,
+            "shadow_achieved": sc_counted["shadow_filter_tests"] * 10 / max(s_s, 1e-12) / 1e9,
+            "shadow_frac": sc_counted["shadow_filter_tests"] * 10 / max(s_s, 1e-12) / peak,
+            "shadow_note": "shadow rays stop at their first occluder; their lanes idle until the segment ends, and "
+                           "only the tests up to the occluder are counted",
+        }
     e2e_wall_max = reduce(e2e_wall, "max")
     e2e_dev_ms_max = reduce(e2e_dev_ms, "max")
     d2h_all = reduce(d2h, "sum")
@@ -491,6 +535,8 @@ def gpu_arm(args, rank, world, local_rank):
                 "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
             },
         }
+        if scan is not None:
+            line["roofline_scan"] = scan
         if assembled_ok is not None:
             line["config"]["assembled_frame_equals_single_gpu"] = assembled_ok
         if world == 1 and not args.no_cpu_baseline:
@@ -522,6 +568,7 @@ def main():
     ap.add_argument("--accel", default="auto", choices=("auto", "exact", "linear", "bvh", "bvh_mega", "grid"))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline sample at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scan-roofline", action="store_true", help="skip the brute-force-scan roofline band")
     args = ap.parse_args()
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))

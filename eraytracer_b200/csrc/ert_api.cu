@@ -18,8 +18,10 @@
 #include "bvh_build.h"
 #include "light_grid.h"
 #include "cell_grid.h"
+#include "host_threads.h"
 #include "ert_device.cuh"
 #include "ert_wavefront.cuh"
+#include "ert_scan.cuh"
 
 // ERT_ACCEL_LINEAR: scenes up to this many spheres stay in the single-launch tiled kernel (one resident
 // tile, no queue traffic); larger ones run the wavefront with the brute-force scan kernels.
@@ -65,6 +67,7 @@ struct HostScene {
     std::vector<double> sph_mat;       // [n][6]
     std::vector<int> sph_order;
     std::vector<float> sph_filter;     // [n][4]
+    std::vector<float> sph_pairs;      // pair-interleaved, padded to whole scan tiles (ert_scan.cuh)
     std::vector<float> leaf_filter;    // [n][4]
     Bvh bvh;
     std::vector<LightGrid> lgrids;     // direction grids of the first lights (shadow queries)
@@ -82,6 +85,8 @@ struct Slot {
     // wavefront queues (ERT_ACCEL_BVH), allocated on first use
     void *wf_mem = nullptr;
     size_t wf_cap = 0;
+    void *scan_mem = nullptr;                      // partial results of the brute-force scan (ert_scan.cuh)
+    size_t scan_cap = 0;
     unsigned int *wf_ctr = nullptr;
     int wf_ctr_depth = 0;
     unsigned int *wf_ctr_host = nullptr;           // pinned, for the early-out check of deep recursions
@@ -251,20 +256,31 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         }
         radii[(size_t)k] = s.radius;
     }
-    std::thread bvh_thread, cell_thread;
-    struct Joiner {                              // joins on every way out of this function
-        std::thread &a, &b;
-        ~Joiner() { if (a.joinable()) a.join(); if (b.joinable()) b.join(); }
-    } joiner{bvh_thread, cell_thread};
+    {
+        // the same filter spheres pair-interleaved for the packed brute-force scan; the padding never passes
+        // stage 1 (R = -3e38)
+        const size_t n_tiles = ((size_t)h.n_spheres + kScanTile - 1) / kScanTile;
+        h.sph_pairs.assign(n_tiles * kScanTile * 4, 0.f);
+        for (size_t k = 0; k < n_tiles * kScanTile; k++) {
+            float *o = &h.sph_pairs[(k >> 1) * 8 + (k & 1)];
+            if (k < (size_t)h.n_spheres) {
+                const float *f = &h.sph_filter[k * 4];
+                o[0] = f[0]; o[2] = f[1]; o[4] = f[2]; o[6] = f[3];
+            } else {
+                o[0] = o[2] = o[4] = 0.f; o[6] = -3.0e38f;
+            }
+        }
+    }
+    // The builders (BVH, cell grid, one direction grid per light) are independent and run side by side; an
+    // exception in any of them (std::bad_alloc, std::system_error) comes back through join() below.
+    WorkerGroup builders;
     {
         // tuning knobs of the BVH builder (defaults are the measured best, DESIGN.md "BVH")
         int leaf_max = kBvhLeafMax;
         float trav_cost = kBvhTravCost;
         if (const char *e = getenv("ERT_BVH_LEAF_MAX")) leaf_max = atoi(e);
         if (const char *e = getenv("ERT_BVH_TRAV_COST")) trav_cost = (float)atof(e);
-        // the three builders (BVH, cell grid, direction grids) are independent: the BVH and the cell grid
-        // are built on their own threads while this one goes on to the direction grids
-        bvh_thread = std::thread([&h, &centers, &radii, leaf_max, trav_cost] {
+        builders.spawn([&h, &centers, &radii, leaf_max, trav_cost] {
             build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
         });
     }
@@ -288,10 +304,11 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         if (const char *e = getenv("ERT_CELL_GRID_DENSITY")) density = atof(e);
         const char *off = getenv("ERT_CELL_GRID");
         if (!(off && atoi(off) == 0))
-            cell_thread = std::thread([&h, &centers, &radii, density] {
+            builders.spawn([&h, &centers, &radii, density] {
                 build_cell_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, h.abs_max, density, h.cgrid);
             });
     }
+    std::vector<char> lg_built;
     {
         // direction grids for shadow rays: worth their memory once a walk through the BVH costs more
         // than a handful of candidate tests; ERT_LIGHT_GRID_RES=0 turns them off
@@ -300,12 +317,25 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         res = std::min(std::max(res, 0), 1024);
         int n_grids = (res > 0 && h.n_spheres >= kLightGridMinSpheres) ? std::min(h.n_lights, kMaxLightGrids) : 0;
         h.lgrids.resize((size_t)n_grids);
+        lg_built.assign((size_t)n_grids, 0);
         for (int g = 0; g < n_grids; g++)
-            build_light_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres, &h.lights[(size_t)g * 9 + 3],
-                             res, h.lgrids[(size_t)g]);
+            builders.spawn([&h, &centers, &radii, &lg_built, g, res] {
+                lg_built[(size_t)g] = build_light_grid(centers.data(), radii.data(), h.sph_filter.data(), h.n_spheres,
+                                                       &h.lights[(size_t)g * 9 + 3], res, h.lgrids[(size_t)g]) ? 1 : 0;
+            });
     }
-    if (bvh_thread.joinable()) bvh_thread.join();
-    if (cell_thread.joinable()) cell_thread.join();
+    builders.join();
+    {
+        // the device code gives the first lg_count lights a grid: a light whose grid went over its entry budget
+        // ends the run of grids
+        size_t keep = 0;
+        while (keep < lg_built.size() && lg_built[keep]) keep++;
+        h.lgrids.resize(keep);
+    }
+    // the traversal stacks hold kBvhStack entries; the builder's depth bound (SAH levels + median levels) keeps
+    // trees far below that, and a tree that is not must not be walked with a stack that silently drops subtrees
+    if (h.bvh.depth >= kBvhStack)
+        return fail(ERT_ERR_BADARG, "sphere BVH is deeper than the traversal stack");
     h.leaf_filter.resize((size_t)h.n_spheres * 4);
     for (int64_t k = 0; k < h.n_spheres; k++)
         memcpy(&h.leaf_filter[(size_t)k * 4], &h.sph_filter[(size_t)h.bvh.leaf_prim[(size_t)k] * 4], 16);
@@ -349,6 +379,7 @@ int upload_scene(ert_scene *s)
     UP(h.sph_mat, sph_mat, double);
     UP(h.sph_order, sph_order, int);
     UP(h.sph_filter, sph_filter, float);
+    UP(h.sph_pairs, sph_pairs, float);
     UP(h.leaf_filter, leaf_filter, float);
     UP(h.bvh.leaf_prim, leaf_sph, int);
     UP(h.bvh.nodes, nodes, BvhNode);
@@ -458,14 +489,22 @@ int upload_scene(ert_scene *s)
         if ((rc = carve((const void *)wf_trace_path_refill<false, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, true>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, false>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        CU(cudaFuncSetAttribute(wf_scan_path<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaFuncSetAttribute(wf_scan_path<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaFuncSetAttribute(wf_scan_path<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaFuncSetAttribute(wf_scan_path<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaFuncSetAttribute(wf_scan_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaFuncSetAttribute(wf_scan_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_scan_path<false, false>, kScanThreads, kScanSmem));
-        s->wf_grid_scan = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaFuncSetAttribute(wf_scan<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaFuncSetAttribute(wf_scan<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_scan<false, false, false>, kScanThreads, kScanSmem));
+        int nb2 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, wf_scan<true, false, false>, kScanThreads, kScanSmem));
+        // Several short blocks per resident slot: the hardware hands a new block to an SM as soon as one retires, so
+        // the SM stays full until the grid drains (with exactly one block per slot the warp schedulers let some
+        // blocks run ahead and the launch ends with one or two warps per scheduler: 2.8 of 4 resident on average,
+        // FMA pipe 75 % busy, profiles/r02_c4_scan_full.txt)
+        int scan_waves = 8;
+        if (const char *e = getenv("ERT_SCAN_WAVES")) scan_waves = std::min(std::max(atoi(e), 1), 64);
+        s->wf_grid_scan = prop.multiProcessorCount * std::max(std::min(nb, nb2), 1) * scan_waves;
     }
     return ERT_OK;
 }
@@ -479,6 +518,7 @@ void destroy(ert_scene *s)
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         if (sl.fb) cudaFree(sl.fb);
         if (sl.wf_mem) cudaFree(sl.wf_mem);
+        if (sl.scan_mem) cudaFree(sl.scan_mem);
         if (sl.wf_ctr) cudaFree(sl.wf_ctr);
         if (sl.wf_ctr_host) cudaFreeHost(sl.wf_ctr_host);
         if (sl.wf_ctr_all_host) cudaFreeHost(sl.wf_ctr_all_host);
@@ -579,7 +619,7 @@ void launch_render(int accel, dim3 grid, cudaStream_t st, const DevScene &d, con
 // ---- wavefront frame (ERT_ACCEL_BVH) ------------------------------------------------------
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
+int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf, bool scan)
 {
     int tiles_x = (fp.width + 7) / 8, tiles_y = (fp.local_rows + 3) / 4;
     size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
@@ -624,6 +664,25 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf)
     wf.hist = (unsigned int *)(base + o_hist);
     wf.sums = wf.hist + kSortCells;
     wf.ctr = sl.wf_ctr;
+    wf.sp_best = nullptr; wf.sp_t = nullptr; wf.sp_occ = nullptr;
+    if (scan) {
+        // per path ray its nearest hit so far; per shadow ray the target's Distance and the occluded flag
+        if (n_pad * L >= ((size_t)1 << 32)) return fail(ERT_ERR_BADARG, "frame part has more than 2^32 shadow rays per bounce");
+        const size_t o_best = 0, o_t = align_up(n_pad * sizeof(ScanBest), 256);
+        const size_t o_occ = o_t + align_up(n_pad * L * sizeof(double), 256);
+        const size_t need = o_occ + align_up(n_pad * L, 256);
+        if (sl.scan_cap < need) {
+            if (sl.scan_mem) CU(cudaFree(sl.scan_mem));
+            sl.scan_mem = nullptr; sl.scan_cap = 0;
+            if (cudaMalloc(&sl.scan_mem, need) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ERT_ERR_NOMEM, "out of device memory for the results of the brute-force scan");
+            }
+            sl.scan_cap = need;
+        }
+        unsigned char *sb = (unsigned char *)sl.scan_mem;
+        wf.sp_best = (ScanBest *)(sb + o_best); wf.sp_t = (double *)(sb + o_t); wf.sp_occ = sb + o_occ;
+    }
     return ERT_OK;
 }
 
@@ -634,7 +693,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     WfBuf wf{};
     int rc;
     const FrameParams &fp = fp_in;
-    if ((rc = wf_prepare(s, sl, fp, wf)) != ERT_OK) return rc;
+    if ((rc = wf_prepare(s, sl, fp, wf, scan)) != ERT_OK) return rc;
     cudaStream_t st = sl.stream;
     FrameParams fps = fp;                           // shadow kernels count into the second counter set
     fps.counters = fp.counters + CNT_N;
@@ -666,7 +725,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     static const int cells_from = getenv("ERT_CELLS_FROM") ? atoi(getenv("ERT_CELLS_FROM")) : 0;
     static const int cells_refill_from = getenv("ERT_CELLS_REFILL_FROM") ? atoi(getenv("ERT_CELLS_REFILL_FROM")) : ERT_WF_REFILL_FROM;
     const bool shadows_walk = !no_grid ? d.lg_count < d.n_lights : true;
-    const bool no_sort = unsorted || (!shadows_walk && !force_sort) || getenv("ERT_WF_NO_SORT") != nullptr;
+    static const bool env_no_sort = getenv("ERT_WF_NO_SORT") != nullptr;
+    const bool no_sort = unsorted || (!shadows_walk && !force_sort) || env_no_sort;
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -687,8 +747,15 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
         const bool sort = b >= 1 && !no_sort && !scan;
-        if (scan && b == 0) wf_scan_path<true, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
-        else if (scan) wf_scan_path<false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
+        if (scan) {
+            // planes/triangles seed every ray's result (counted with the other kernels), then every ray meets every sphere
+            if (b == 0) wf_scan_init<false, true, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fp, wf, b);
+            else wf_scan_init<false, false, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fp, wf, b);
+            n++;
+            TICK(2);
+            if (b == 0) wf_scan<false, true, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
+            else wf_scan<false, false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fp, wf, b);
+        }
         else if (cells && b >= cells_from) {
             // path rays step through the cell grid (ERT_ACCEL_GRID)
             if (b == 0) wf_trace_path<true, COUNT, true, true><<<s->wf_grid[4], kWfThreads, 0, st>>>(d, fp, wf, b);
@@ -707,6 +774,12 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         TICK(0);
         WF_CHECK("wf_trace_path");
         if (d.n_lights == 0) break;          // the fold over no lights is black (erl:211-252)
+        if (scan) {
+            // results to the arrays the hit emission reads (counted with it)
+            if (b == 0) wf_scan_finish<false, true><<<s->wf_grid[3], 256, 0, st>>>(d, wf, b);
+            else wf_scan_finish<false, false><<<s->wf_grid[3], 256, 0, st>>>(d, wf, b);
+            n++;
+        }
         if (emitted) {
             n--;                                 // no separate launch
         } else if (b == 0) {
@@ -724,11 +797,20 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         n++;
         TICK(2);
         WF_CHECK("wf_emit_hits / wf_bin_*");
-        if (scan) wf_scan_shadow<COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fps, wf, b);
+        if (scan) {
+            wf_scan_init<true, false, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fps, wf, b);
+            n++;
+            TICK(2);
+            wf_scan<true, false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fps, wf, b);
+        }
         else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
         TICK(1);
         WF_CHECK("wf_trace_shadow");
+        if (scan) {
+            wf_scan_finish<true, false><<<s->wf_grid[3], 256, 0, st>>>(d, wf, b);
+            n++;
+        }
         wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
         n += 2;
         TICK(2);
@@ -832,10 +914,19 @@ int ert_scene_create(const ert_scene_desc *desc, int device, ert_scene **out)
     } catch (const std::bad_alloc &) {
         delete s;
         return fail(ERT_ERR_NOMEM, "out of host memory while flattening the scene");
+    } catch (const std::exception &e) {
+        delete s;
+        return fail(ERT_ERR_NOMEM, std::string("scene build failed: ") + e.what());
     }
     if (rc != ERT_OK) { delete s; return rc; }
     if ((rc = check_device(device)) != ERT_OK) { delete s; return rc; }
-    if ((rc = upload_scene(s)) != ERT_OK) {
+    try {
+        rc = upload_scene(s);
+    } catch (const std::exception &e) {
+        g_err = std::string("out of host memory while uploading the scene: ") + e.what();
+        rc = ERT_ERR_NOMEM;
+    }
+    if (rc != ERT_OK) {
         std::string keep = g_err;
         destroy(s);
         g_err = keep;
@@ -856,11 +947,17 @@ int ert_scene_clone(const ert_scene *src, int device, ert_scene **out)
     s->device = device;
     try {
         s->host = src->host;
-    } catch (const std::bad_alloc &) {
+    } catch (const std::exception &) {
         delete s;
         return fail(ERT_ERR_NOMEM, "out of host memory");
     }
-    if ((rc = upload_scene(s)) != ERT_OK) {
+    try {
+        rc = upload_scene(s);
+    } catch (const std::exception &e) {
+        g_err = std::string("out of host memory while uploading the scene: ") + e.what();
+        rc = ERT_ERR_NOMEM;
+    }
+    if (rc != ERT_OK) {
         std::string keep = g_err;
         destroy(s);
         g_err = keep;
@@ -1157,9 +1254,12 @@ int ert_l2_flush(int device)
     int rc;
     if ((rc = check_device(device)) != ERT_OK) return rc;
     CU(cudaSetDevice(device));
-    static thread_local void *buf[16] = {nullptr};
+    // one buffer per device for the life of the process, whatever thread calls
+    static void *buf[16] = {nullptr};
+    static std::mutex buf_mu;
     const size_t bytes = (size_t)256 << 20;
     if (device >= 16) return fail(ERT_ERR_BADARG, "device index too large for the flush buffers");
+    std::lock_guard<std::mutex> lock(buf_mu);
     if (!buf[device]) CU(cudaMalloc(&buf[device], bytes));
     l2_flush_kernel<<<1184, 256>>>((uint4 *)buf[device], bytes / 16);
     CU(cudaGetLastError());

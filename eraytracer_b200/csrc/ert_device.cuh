@@ -44,6 +44,8 @@ struct DevScene {
     const double *sph_mat;       // [n][6] colour rgb, specular_power, shininess, reflectivity
     const int *sph_order;        // list position
     const float4 *sph_filter;    // {fl(cx), fl(cy), fl(cz), R} — see make_filter_sphere()
+    const float4 *sph_pairs;     // the same list pair-interleaved for the packed scan (ert_scan.cuh): spheres 2p, 2p+1 as
+                                 // {cx0,cx1,cy0,cy1},{cz0,cz1,R0,R1}; padded to whole tiles with spheres that never pass
     // BVH over spheres
     const BvhNode *nodes;
     int n_nodes;
@@ -422,7 +424,7 @@ __device__ __forceinline__ void scan_spheres_bvh(const DevScene &sc, d3 O, d3 D,
             if (h0 && h1) {
                 bool swap = tn1 < tn0;
                 int nearc = swap ? ch.y : ch.x, farc = swap ? ch.x : ch.y;
-                if (sp < kBvhStack) stack[sp++] = farc;
+                if (sp < kBvhStack) stack[sp++] = farc;      // always true: ert_scene_create rejects trees of depth >= kBvhStack
                 node = nearc;
                 continue;
             } else if (h0) { node = ch.x; continue; }

@@ -49,6 +49,12 @@ struct alignas(32) HitTail {
 };
 static_assert(sizeof(HitHead) == 32 && sizeof(HitTail) == 64, "hit records are 32 + 64 bytes");
 
+// nearest hit of one path ray of the brute-force scan: 16 bytes, one 128-bit compare-and-swap
+struct alignas(16) ScanBest {
+    double t;
+    int order, obj;
+};
+
 struct WfBuf {
     int n_pad;                  // pixels of this part padded to whole 8x4 tiles: tiles * 32
     int tiles_x;                // tiles per row of tiles
@@ -67,6 +73,10 @@ struct WfBuf {
     unsigned int *ctr;          // [depth][kWfCtr] queue lengths and work cursors
     unsigned int *hist;         // [kSortCells] cell histogram -> offsets -> scatter cursors
     unsigned int *sums;         // [kSortBlocks] per-block totals of the histogram scan
+    // brute-force scan (ert_scan.cuh), allocated for ERT_ACCEL_LINEAR frames only
+    ScanBest *sp_best;      // [n_pad] nearest hit of each path ray while candidates fold into it
+    double *sp_t;               // [n_pad * lights] Distance of each shadow ray's target
+    unsigned char *sp_occ;      // [n_pad * lights] 1: something is nearer than the target (or the target is missed)
 };
 enum WfCtr : int { WF_NHITS = 0, WF_NNEXT = 1, WF_FETCH_PATH = 2 /* 64-bit */, WF_FETCH_SHADOW = 4 /* 64-bit */, kWfCtr = 8 };
 constexpr int kWfThreads = 256;
@@ -284,7 +294,7 @@ __device__ __forceinline__ bool trav_step(Trav<ANY> &tr, int *stack, const DevSc
         if (h0 && h1) {
             bool swap = tn1 < tn0;
             tr.node = swap ? ch.y : ch.x;
-            if (tr.sp < kBvhStack) {
+            if (tr.sp < kBvhStack) {                     // always true: ert_scene_create rejects trees of depth >= kBvhStack
                 stack[tr.sp] = swap ? ch.x : ch.y;
                 tr.sp++;
             }
@@ -1301,290 +1311,6 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 __syncwarp();
             }
         }
-    }
-    flush_counters<COUNT>(fp, (int)rays, tl);
-}
-
-// ------------------------------------------------------------------ brute-force scan (ERT_ACCEL_LINEAR)
-// The reference's linear scan (erl:300-346) as a wavefront: same queues, same set-up, but every
-// ray tests EVERY sphere — the FP32 filter over tiles of the list-ordered filter array, streamed
-// global -> shared by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) into a double buffer
-// that a block of 256 rays shares.  This is the kernel the FP32-issue roofline is about: 10
-// FP32-pipe instructions + 1 compare + 1/UNROLL of a broadcast LDS.128 per (ray, sphere).
-// A block takes kScanThreads consecutive queue entries at a time (one ray per thread).  128 rays on
-// tiles of 1024 spheres, six blocks per SM, beat 256 rays on tiles of 2048, two blocks: the barrier
-// per tile then holds four warps instead of eight and 24 warps per SM hide the LDS latency
-// (wf_scan_path 59 -> 61 % of the FP32 issue peak on C3).
-#ifndef ERT_SCAN_TILE
-#define ERT_SCAN_TILE 1024
-#endif
-#ifndef ERT_SCAN_MINBLOCKS
-#define ERT_SCAN_MINBLOCKS 6
-#endif
-#ifndef ERT_SCAN_THREADS
-#define ERT_SCAN_THREADS 128
-#endif
-constexpr int kScanThreads = ERT_SCAN_THREADS;            // rays per block of the scan kernels (<= kWfThreads)
-static_assert(kScanThreads <= kWfThreads && kScanThreads % 32 == 0, "the ray slots are laid out for kWfThreads");
-constexpr int kScanTile = ERT_SCAN_TILE;                  // filter spheres per buffer (16 B each)
-static_assert(kScanTile % 8 == 0, "tiles are whole groups");
-constexpr int kScanSmem = 2 * kScanTile * 16;             // dynamic shared memory of the scan kernels
-
-struct ScanPipe {
-    float4 *tiles;
-    uint64_t *bars;
-    uint32_t phase_bits;
-};
-
-// Streams all tiles once; `body(tile, count, base_index)` runs for every tile while `active`.
-// Every thread of the block must call this together.  ANY: the block stops streaming once no thread is active.
-template <class Body>
-__device__ __forceinline__ void scan_all_tiles(const DevScene &sc, ScanPipe &pp, bool &active, Body body)
-{
-    const int n = sc.n_spheres;
-    const int n_tiles = (n + kScanTile - 1) / kScanTile;
-    if (threadIdx.x == 0 && n_tiles > 0) {
-        const int cnt = min(kScanTile, n);
-        mbar_expect_tx(&pp.bars[0], cnt * 16u);
-        bulk_g2s(pp.tiles, sc.sph_filter, cnt * 16u, &pp.bars[0]);
-    }
-    for (int t = 0; t < n_tiles; t++) {
-        const int buf = t & 1;
-        bool more = true;
-        if (t + 1 < n_tiles) {
-            more = __syncthreads_or(active);              // also: everyone is done with the other buffer
-            if (more && threadIdx.x == 0) {
-                const int cnt = min(kScanTile, n - (t + 1) * kScanTile);
-                mbar_expect_tx(&pp.bars[buf ^ 1], cnt * 16u);
-                bulk_g2s(pp.tiles + (buf ^ 1) * kScanTile, sc.sph_filter + (size_t)(t + 1) * kScanTile, cnt * 16u,
-                         &pp.bars[buf ^ 1]);
-            }
-        }
-        mbar_wait(&pp.bars[buf], (pp.phase_bits >> buf) & 1u);
-        pp.phase_bits ^= 1u << buf;
-        if (active) body(pp.tiles + buf * kScanTile, min(kScanTile, n - t * kScanTile), t * kScanTile);
-        if (!more) break;
-    }
-    __syncthreads();                                      // the buffers are free for the next batch
-}
-
-// The filter over one tile for one ray.  A group of kScanGroup spheres costs 10 FP32-pipe
-// instructions and one LDS.128 per sphere plus ONE 3-input max per two spheres: the group keeps only
-// the largest stage-1 value v, and one compare per group decides whether any of its spheres can
-// pass (v >= -theta).  Only then — a few groups per thousand — are its spheres looked at one by one
-// (stage 1 again, stage 2, literal FP64 test).  fmaxf drops NaNs, and the filter must pass them
-// (DESIGN.md "Filter bounds"), so a ray for which v could overflow to Inf - Inf takes every group the
-// slow way (`m0` = +Inf): coordinates beyond 1e17, never in practice.
-#ifndef ERT_SCAN_GROUP
-#define ERT_SCAN_GROUP 16
-#endif
-constexpr int kScanGroup = ERT_SCAN_GROUP;
-constexpr int kScanQuarters = 4, kScanQuarter = kScanGroup / kScanQuarters;
-static_assert(kScanGroup % 8 == 0 && kScanTile % kScanGroup == 0, "quarters are whole pairs, tiles whole groups");
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void scan_tile(const DevScene &sc, const SRay &f, const RaySlot &ray, const float4 *tile,
-                                          int cnt, int base, int skip_obj, int seed_obj, Hit &best, float &cullk,
-                                          bool &active, Tally<COUNT> &tl)
-{
-    const float ntheta = -f.theta;
-    const float oabs = fmaxf(fmaxf(fabsf(f.ox), fabsf(f.oy)), fabsf(f.oz));
-    const float m0 = (oabs + sc.abs_max < 1e17f) ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000);
-#pragma unroll 1
-    for (int k0 = 0; k0 < cnt; k0 += kScanGroup) {
-        // one running maximum per quarter of the group: the rare slow path then looks at 4 spheres, not 16
-        float mq[kScanQuarters];
-#pragma unroll
-        for (int q = 0; q < kScanQuarters; q++) {
-            float m = m0;
-#pragma unroll
-            for (int u = q * kScanQuarter; u < (q + 1) * kScanQuarter; u += 2) {
-                // past `cnt` the buffer holds stale spheres: the slow path below stops at cnt
-                const float4 s0 = tile[k0 + u], s1 = tile[k0 + u + 1];
-                const float cx0 = s0.x - f.ox, cy0 = s0.y - f.oy, cz0 = s0.z - f.oz;
-                const float cx1 = s1.x - f.ox, cy1 = s1.y - f.oy, cz1 = s1.z - f.oz;
-                const float b0 = __fmaf_rn(f.dz, cz0, __fmaf_rn(f.dy, cy0, f.dx * cx0));
-                const float b1 = __fmaf_rn(f.dz, cz1, __fmaf_rn(f.dy, cy1, f.dx * cx1));
-                const float w0 = __fmaf_rn(cx0, cx0, __fmaf_rn(cy0, cy0, __fmaf_rn(cz0, cz0, -s0.w)));
-                const float w1 = __fmaf_rn(cx1, cx1, __fmaf_rn(cy1, cy1, __fmaf_rn(cz1, cz1, -s1.w)));
-                const float v0 = __fmaf_rn(b0, b0, -w0), v1 = __fmaf_rn(b1, b1, -w1);
-                m = fmaxf(fmaxf(m, v0), v1);
-            }
-            mq[q] = m;
-        }
-        float mall = mq[0];
-#pragma unroll
-        for (int q = 1; q < kScanQuarters; q++) mall = fmaxf(mall, mq[q]);
-        if (mall < ntheta) continue;                     // no sphere of the group passes stage 1
-        unsigned int qmask = 0u;
-#pragma unroll
-        for (int q = 0; q < kScanQuarters; q++) qmask |= (mq[q] < ntheta) ? 0u : (1u << q);
-#pragma unroll 1
-        for (int k = k0; k < min(k0 + kScanGroup, cnt); k++) {
-            if (!((qmask >> ((k - k0) / kScanQuarter)) & 1u)) { k += kScanQuarter - 1; continue; }
-            const float4 fs = tile[k];
-            float b, v;
-            if (!filter_stage1(f, fs, b, v)) continue;
-            if (!filter_stage2(f, fs, b, v, cullk)) continue;
-            const int sph = base + k;
-            const int code = obj_code(OBJ_SPHERE, sph);
-            if (code == skip_obj) continue;
-            double t;
-            TALLY(exact_sph);
-            if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
-                const int ord = sc.sph_order[sph];
-                if (better(t, ord, best)) {
-                    best.t = t; best.order = ord; best.obj = code;
-                    cullk = cullk_from(f, ray.inv_sqrt_a(), best);
-                    if constexpr (ANY) {                  // a shadow ray only asks whether one exists
-                        if constexpr (COUNT) tl.filter += min(k0 + kScanGroup, cnt);
-                        active = false;
-                        return;
-                    }
-                }
-            }
-        }
-    }
-    if constexpr (COUNT) tl.filter += cnt;
-    (void)seed_obj;
-}
-
-template <bool FIRST, bool COUNT>
-__global__ void __launch_bounds__(kScanThreads, ERT_SCAN_MINBLOCKS)
-wf_scan_path(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
-             const __grid_constant__ WfBuf wf, int bounce)
-{
-    extern __shared__ __align__(128) unsigned char scan_smem[];
-    __shared__ double slots[kRaySlotDoubles][kWfThreads];
-    __shared__ __align__(8) uint64_t bars[2];
-    __shared__ unsigned long long s_base;
-    RaySlot ray;
-    ray.p = &slots[0][threadIdx.x];
-    ScanPipe pp;
-    pp.tiles = reinterpret_cast<float4 *>(scan_smem);
-    pp.bars = bars;
-    pp.phase_bits = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
-    const unsigned long long n = FIRST ? (unsigned long long)wf.n_pad
-                                       : (unsigned long long)wf.ctr[(bounce - 1) * kWfCtr + WF_NNEXT];
-    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_PATH);
-    Tally<COUNT> tl;
-    unsigned int rays = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kScanThreads);
-        __syncthreads();
-        const unsigned long long base = s_base;
-        if (base >= n) break;
-        const unsigned long long i64 = base + threadIdx.x;
-        bool valid = i64 < n;
-        const unsigned int i = (unsigned int)i64;
-        Hit best;
-        best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
-        SRay f;
-        float cullk = 0.f;
-        bool active = false;
-        if (valid) {
-            int pid;
-            d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
-            path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
-            if (valid) {
-                rays++;
-                scan_others<COUNT>(sc, O, D, best, -1, tl);
-                double a, inv;
-                make_sray(sc, O, D, f, a, inv);
-                ray.put(O, D, a, inv);
-                cullk = cullk_from(f, inv, best);
-                active = sc.n_spheres > 0;
-            }
-        }
-        scan_all_tiles(sc, pp, active, [&](const float4 *tile, int cnt, int tbase) {
-            scan_tile<false, COUNT>(sc, f, ray, tile, cnt, tbase, -1, -1, best, cullk, active, tl);
-        });
-        if (i64 < n) {
-            __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
-            __stcs(wf.res_t + i, best.t);
-        }
-    }
-    flush_counters<COUNT>(fp, (int)rays, tl);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kScanThreads, ERT_SCAN_MINBLOCKS)
-wf_scan_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
-               const __grid_constant__ WfBuf wf, int bounce)
-{
-    extern __shared__ __align__(128) unsigned char scan_smem[];
-    __shared__ double slots[kRaySlotDoubles][kWfThreads];
-    __shared__ __align__(8) uint64_t bars[2];
-    __shared__ unsigned long long s_base;
-    RaySlot ray;
-    ray.p = &slots[0][threadIdx.x];
-    ScanPipe pp;
-    pp.tiles = reinterpret_cast<float4 *>(scan_smem);
-    pp.bars = bars;
-    pp.phase_bits = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
-    const unsigned int n_hits = ctr[WF_NHITS];
-    const unsigned long long total = (unsigned long long)n_hits * (unsigned long long)sc.n_lights;
-    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_SHADOW);
-    const size_t np = (size_t)wf.n_pad;
-    Tally<COUNT> tl;
-    unsigned int rays = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned long long)kScanThreads);
-        __syncthreads();
-        const unsigned long long base = s_base;
-        if (base >= total) break;
-        const unsigned long long j = base + threadIdx.x;
-        const bool valid = j < total;
-        unsigned int l = 0, h = 0;
-        Hit best;
-        best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
-        SRay f;
-        float cullk = 0.f;
-        bool active = false, lit = false;
-        int target = -1;
-        if (valid) {
-            l = (unsigned int)(j / n_hits);
-            h = (unsigned int)(j - (unsigned long long)l * n_hits);
-            rays++;
-            const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
-            d3 P = mk(r0.x, r0.y, r0.z);
-            target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
-            const int order = (int)(__double_as_longlong(r0.w) >> 32);
-            const double *lt = sc.lights + 9 * (size_t)l;
-            d3 O = mk(lt[3], lt[4], lt[5]);
-            d3 D = vnormalize(vsub(P, O));                         // erl:257-260
-            double a = D.x * D.x + D.y * D.y + D.z * D.z;
-            double t;
-            if (object_exact(sc, target, O, D, a, t)) {              // erl:263 needs the target hit
-                best.t = t; best.order = order; best.obj = target;
-                scan_others<COUNT>(sc, O, D, best, target, tl);
-                lit = best.obj == target;
-                if (lit && sc.n_spheres > 0) {
-                    double a2, inv;
-                    make_sray(sc, O, D, f, a2, inv);
-                    ray.put(O, D, a2, inv);
-                    cullk = cullk_from(f, inv, best);
-                    active = true;
-                }
-            }
-        }
-        scan_all_tiles(sc, pp, active, [&](const float4 *tile, int cnt, int tbase) {
-            scan_tile<true, COUNT>(sc, f, ray, tile, cnt, tbase, target, target, best, cullk, active, tl);
-        });
-        if (valid) wf.lit[(size_t)l * np + h] = lit && best.obj == target;
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
 }

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <thread>
 
+#include "host_threads.h"
+
 namespace ert {
 namespace {
 
@@ -51,7 +53,7 @@ int64_t light_grid_cell(const double d[3], int res)
     return ((int64_t)face * res + cell_index(v, res)) * res + cell_index(u, res);
 }
 
-void build_light_grid(const double *centers, const double *radii, const float *filter, int64_t n,
+bool build_light_grid(const double *centers, const double *radii, const float *filter, int64_t n,
                       const double light[3], int res, LightGrid &out)
 {
     out.res = res;
@@ -92,12 +94,7 @@ void build_light_grid(const double *centers, const double *radii, const float *f
             }
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < n_thr; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto &x : th) x.join();
-    }
+    parallel_threads(n_thr, work);
     for (auto &v : always) out.always.insert(out.always.end(), v.begin(), v.end());
 
     // pass 2: counting sort of (cell, sphere) pairs
@@ -108,6 +105,14 @@ void build_light_grid(const double *centers, const double *radii, const float *f
                 for (int u = q.u0; u <= q.u1; u++) row[u]++;
             }
     uint64_t total = 0;
+    for (size_t k = 0; k < n_cells; k++) total += out.cell_off[k];
+    if (total > kLightGridMaxEntries) {
+        // many spheres close to the light: the grid would cost more memory than it saves walks (and its 32-bit
+        // offsets would wrap past 2^32); this light's shadow rays walk the BVH instead
+        out = LightGrid{};
+        return false;
+    }
+    total = 0;
     for (size_t k = 0; k < n_cells; k++) { uint32_t c = out.cell_off[k]; out.cell_off[k] = (uint32_t)total; total += c; }
     out.cell_off[n_cells] = (uint32_t)total;
     out.entries.assign((size_t)total, LightGridEntry{0, 0.f});
@@ -136,14 +141,10 @@ void build_light_grid(const double *centers, const double *radii, const float *f
                 });
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (unsigned t = 1; t < n_thr; t++) th.emplace_back(sort_range, n_cells * t / n_thr, n_cells * (t + 1) / n_thr);
-        sort_range(0, n_cells / n_thr);
-        for (auto &x : th) x.join();
-    }
+    parallel_threads(n_thr, [&](unsigned t) { sort_range(n_cells * t / n_thr, n_cells * (t + 1) / n_thr); });
     out.fs.resize((size_t)total * 4);
     for (size_t e = 0; e < (size_t)total; e++) memcpy(&out.fs[4 * e], filter + 4 * (size_t)out.entries[e].sphere, 16);
+    return true;
 }
 
 }  // namespace ert

@@ -16,6 +16,7 @@ namespace ert {
 constexpr int kLightGridRes = 128;          // default cells per cube-face edge
 constexpr int kMaxLightGrids = 8;           // lights beyond this use the BVH for their shadow rays
 constexpr int kLightGridMinSpheres = 64;    // smaller scenes do not need one
+constexpr uint64_t kLightGridMaxEntries = 1ull << 27;   // (cell, sphere) entries per light: 4 GB of candidates
 
 struct LightGridEntry {          // 8 bytes next to a 16-byte filter sphere
     int32_t sphere;              // sphere index (list order among spheres)
@@ -31,7 +32,8 @@ struct LightGrid {
 };
 
 // centers: n*3, radii: n, filter: n*4 (the scene's FP32 filter spheres), light: xyz.
-void build_light_grid(const double *centers, const double *radii, const float *filter, int64_t n,
+// Returns false (and leaves `out` empty) when the grid would need more than kLightGridMaxEntries entries.
+bool build_light_grid(const double *centers, const double *radii, const float *filter, int64_t n,
                       const double light[3], int res, LightGrid &out);
 
 // Face/cell of a direction, shared by the builder's tests and (re-stated) by the device code:

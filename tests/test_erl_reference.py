@@ -1,0 +1,169 @@
+"""Parity pinned to the reference's SOURCE TEXT.
+
+oracle/erlref.py evaluates /root/reference/raytracer.erl itself (tokeniser, parser, Erlang semantics) and is
+checked by the reference's own test-suite run_tests/0 (erl:736-1133).  tests/golden/erl_reference.json holds
+what the reference's functions returned under it for the scenes of tests/erl_scenes.py: whole images through
+raytraced_pixel_list_simple/4, nearest hits through nearest_object_intersecting_ray/2, and the text
+write_pixels_to_ppm/5 wrote.  Here:
+
+  * where the reference is mounted (this container, not the GPU box): the suite is run again, images are
+    re-rendered live and must equal the oracle and the committed file bit for bit;
+  * everywhere: the C oracle, the Python restatement, the product's PPM writer and (gpu) the CUDA path are held
+    to the committed values — all doubles bit for bit on the CPU side; RGB8 equal and |d| <= 1e-9 relative
+    for the GPU (its shading is the forward form, DESIGN.md "Exactness"), (list position, Distance bits) for rays.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import orc, pyoracle
+from erl_scenes import SCENES, scene_records
+from helpers import assert_double_parity, assert_image_parity, quantise
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/raytracer.erl"
+needs_reference = pytest.mark.skipif(not os.path.exists(REF), reason="the reference source is not mounted here")
+
+with open(os.path.join(HERE, "golden", "erl_reference.json")) as _fh:
+    GOLD = json.load(_fh)
+IMAGES = sorted(GOLD["images"])
+
+
+def _module():
+    from oracle import erlref
+    sys.setrecursionlimit(200000)
+    return erlref, erlref.load(REF)
+
+
+def _oracle(name, w, h, depth):
+    recs = scene_records(name)
+    cam = orc.camera_array(recs[0])
+    kind, f = orc.flatten(recs[1:])
+    rgb, rays, _ = orc.render(cam, kind, f, w, h, depth, retrace=True)
+    return rgb
+
+
+def _gold_pixels(key):
+    g = GOLD["images"][key]
+    return g, np.array(g["pixels"], dtype=np.float64)
+
+
+# ------------------------------------------------------------------ the evaluator itself (reference mounted)
+@needs_reference
+def test_the_references_own_suite_passes_under_the_evaluator():
+    erlref, m = _module()
+    assert m.call("run_tests") == erlref.Atom("ok")
+    log = "".join(m.out)
+    assert log.count(" - OK") == 18 and "FAILED" not in log and "Success!" in log
+    assert GOLD["run_tests"] == "ok"
+
+
+@needs_reference
+def test_live_render_from_the_source_equals_the_oracles_and_the_committed_file():
+    erlref, m = _module()
+    from erl_scenes import scene_terms
+    for name, (w, h, depth) in (("demo", (8, 6, 2)), ("stress", (6, 5, 2))):
+        px = m.call("raytraced_pixel_list_simple", w, h, scene_terms(m, name), depth)
+        live = np.array([[float(c) for c in p[1]] for p in px])
+        assert np.array_equal(live, _oracle(name, w, h, depth)), name
+    # one committed image regenerated: the file is what this reference produces
+    g, gold = _gold_pixels("demo_16x12_d5")
+    px = m.call("raytraced_pixel_list_simple", 16, 12, m.call("scene"), 5)
+    assert np.array_equal(np.array([[float(c) for c in p[1]] for p in px]), gold)
+    # the second restatement agrees too
+    sc_py = pyoracle.scene()
+    img = [p[1] for p in pyoracle.raytraced_pixel_list_simple(8, 6, sc_py, 2)]
+    px = m.call("raytraced_pixel_list_simple", 8, 6, m.call("scene"), 2)
+    assert np.array_equal(np.array(img, dtype=np.float64), np.array([[float(c) for c in p[1]] for p in px]))
+
+
+@needs_reference
+def test_scene_function_of_the_source_is_the_demo_scene_of_the_package():
+    erlref, m = _module()
+    from eraytracer_b200 import scene as sc
+    def plain(x):
+        return [plain(y) for y in x] if isinstance(x, (tuple, list)) else x
+    assert erlref.to_py(m.call("scene")) == plain(sc.demo_scene())
+
+
+# ------------------------------------------------------------------ oracle == reference (everywhere)
+@pytest.mark.parametrize("key", IMAGES)
+def test_oracle_equals_the_reference_image_bit_for_bit(key):
+    g, gold = _gold_pixels(key)
+    rgb = _oracle(g["scene"], g["width"], g["height"], g["depth"])
+    assert np.array_equal(rgb, gold), "%d of %d channel values differ" % (int((rgb != gold).sum()), gold.size)
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["rays"]))
+def test_oracle_nearest_hits_equal_the_references(name):
+    g = GOLD["rays"][name]
+    recs = scene_records(name)
+    kind, f = orc.flatten(recs[1:])
+    rays = np.array(g["rays"], dtype=np.float64)
+    idx, t = orc.nearest_batch(rays, kind, f)
+    want_idx = np.array([h[0] for h in g["hits"]])
+    want_t = np.array([h[1] for h in g["hits"]], dtype=np.float64)
+    assert np.array_equal(idx, want_idx)
+    hit = want_idx >= 0
+    assert hit.sum() > len(rays) // 4
+    assert np.array_equal(t[hit], want_t[hit])
+
+
+def test_ppm_writer_writes_the_references_text(tmp_path):
+    from eraytracer_b200 import ppm
+    for key, (w, h) in (("awkward_8x6", (8, 6)), ("demo_8x6_d2", (8, 6))):
+        g = GOLD["ppm"][key]
+        pixels = [(k, tuple(p)) for k, p in enumerate(g["pixels"])]
+        out = tmp_path / (key + ".ppm")
+        ppm.write_pixels_to_ppm(w, h, 255, pixels, str(out))
+        assert out.read_text() == g["text"], key
+    # the quantisation rule the parity metric uses is the writer's (erl:678-680), negative values included
+    g = GOLD["ppm"]["awkward_8x6"]
+    want = [int(tok) for tok in g["text"].split("\n", 3)[3].split()]
+    assert quantise(np.array(g["pixels"])).reshape(-1).tolist() == want
+
+
+# ------------------------------------------------------------------ CUDA path == reference
+GPU_ACCELS = {"demo": ("auto", "exact", "linear", "bvh", "grid"), "pose5": ("auto",), "pose37": ("auto",),
+              "stress": ("auto", "exact", "linear", "bvh", "bvh_mega"), "mini_c3": ("auto", "exact", "linear", "bvh", "grid")}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", IMAGES)
+def test_gpu_equals_the_reference_image(gpu, key):
+    from eraytracer_b200 import scene as sc
+    g, gold = _gold_pixels(key)
+    w, h, depth = g["width"], g["height"], g["depth"]
+    dev = sc.flatten(scene_records(g["scene"])).upload(0)
+    try:
+        for accel in GPU_ACCELS[g["scene"]]:
+            frame, st = dev.render(w, h, depth, fmt="f64", accel=accel)
+            assert_double_parity(frame.reshape(-1, 3), gold)
+            assert np.array_equal(quantise(frame.reshape(-1, 3)), quantise(gold)), (key, accel)
+            rgb8, _ = dev.render(w, h, depth, fmt="rgb8", accel=accel)
+            assert np.array_equal(rgb8.reshape(-1, 3), np.clip(quantise(gold), 0, 255)), (key, accel)
+            assert_image_parity(rgb8.reshape(-1, 3), np.clip(quantise(gold), 0, 255))
+    finally:
+        dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLD["rays"]))
+def test_gpu_nearest_hits_equal_the_references(gpu, name):
+    from eraytracer_b200 import scene as sc
+    g = GOLD["rays"][name]
+    dev = sc.flatten(scene_records(name)).upload(0)
+    rays = np.array(g["rays"], dtype=np.float64)
+    want_idx = np.array([h[0] for h in g["hits"]])
+    want_t = np.array([h[1] for h in g["hits"]], dtype=np.float64)
+    hit = want_idx >= 0
+    try:
+        for accel in ("exact", "linear", "bvh", "bvh_mega", "grid"):
+            order, t = dev.trace_rays(rays, accel=accel)
+            assert np.array_equal(order, want_idx), accel
+            assert np.array_equal(t[hit], want_t[hit]), accel
+    finally:
+        dev.close()

@@ -83,6 +83,36 @@ __global__ void __launch_bounds__(256) k_mix(float *out, int iters, const float 
     if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FFMA2 with scalar FFMA / FMNMX mixed in from independent chains: does anything issue in the shadow of a packed op?
+template <int N2, int N1, int NM>
+__global__ void __launch_bounds__(256) k_mix2(float *out, int iters, const float *in)
+{
+    u64 a[N2 > 0 ? N2 : 1];
+    float b[N1 > 0 ? N1 : 1], c[NM > 0 ? NM : 1];
+    for (int k = 0; k < N2; k++) a[k] = pk(in[0] + threadIdx.x + k, in[0] + k);
+    for (int k = 0; k < N1; k++) b[k] = in[0] + threadIdx.x + 0.5f * k;
+    for (int k = 0; k < NM; k++) c[k] = in[0] + threadIdx.x + 0.25f * k;
+    const u64 m2 = pk(in[1], in[2]), c2 = pk(in[3], in[4]);
+    const float m1 = in[1], c1 = in[3], lim = in[2];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+#pragma unroll
+            for (int j = 0; j < N2; j++) a[j] = fma2(a[j], m2, c2);
+#pragma unroll
+            for (int j = 0; j < N1; j++) b[j] = __fmaf_rn(b[j], m1, c1);
+#pragma unroll
+            for (int j = 0; j < NM; j++) c[j] = fmaxf(fminf(c[j], lim), c[(j + 1) % NM] * 1.0f);
+        }
+    }
+    float s = 0;
+    for (int k = 0; k < N2; k++) { float lo, hi; upk(a[k], lo, hi); s += lo + hi; }
+    for (int k = 0; k < N1; k++) s += b[k];
+    for (int k = 0; k < NM; k++) s += c[k];
+    if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---- 2. the filter loop over a resident tile
 // scalar: tile of float4 {cx, cy, cz, R}; NR rays per thread
 template <int NR>
@@ -222,6 +252,26 @@ int main()
         report(nm, (double)blocks * 256 * iters * 128 * 2, best[1]);
         snprintf(nm, sizeof nm, "10 FFMA2 : 1 FMNMX3 : 1 LDS.128, %d blocks/SM", blocks_per_sm);
         report(nm, (double)blocks * 256 * iters * 80 * 2, best[2]);
+    }
+    {
+        const int blocks = sms * 8;
+        auto mix = [&](const char *name, auto kern, int n2, int n1, int nm) {
+            double best = 1e30;
+            for (int rep = 0; rep < 3; rep++) {
+                CK(cudaEventRecord(e0)); kern<<<blocks, 256>>>(out, iters, in); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+                best = std::min(best, time_ms(e0, e1));
+            }
+            const double fp32 = (double)blocks * 256 * iters * 16 * (2.0 * n2 + n1);
+            printf("%-44s %8.3f ms  %9.1f G FP32 lane-instr/s  (+%d min/max per round)\n", name, best, fp32 / (best * 1e-3) / 1e9, 2 * nm);
+        };
+        mix("8 FFMA2", k_mix2<8, 0, 0>, 8, 0, 0);
+        mix("8 FFMA2 + 4 FFMA", k_mix2<8, 4, 0>, 8, 4, 0);
+        mix("8 FFMA2 + 8 FFMA", k_mix2<8, 8, 0>, 8, 8, 0);
+        mix("4 FFMA2 + 8 FFMA", k_mix2<4, 8, 0>, 4, 8, 0);
+        mix("16 FFMA", k_mix2<0, 16, 0>, 0, 16, 0);
+        mix("8 FFMA2 + 2x2 FMNMX", k_mix2<8, 0, 2>, 8, 0, 2);
+        mix("8 FFMA2 + 4x2 FMNMX", k_mix2<8, 0, 4>, 8, 0, 4);
+        mix("16 FFMA + 4x2 FMNMX", k_mix2<0, 16, 4>, 0, 16, 4);
     }
     CK(cudaGetLastError());
 
