@@ -295,6 +295,8 @@ def gpu_arm(args, rank, world, local_rank):
     common = dict(fmt=fmt, accel=accel, band_rows=band_rows, n_parts=n_parts, part=rank)
     peak = _lib.fp32_peak(local_rank)
     peak_rrr = _lib.fp32_peak_rrr(local_rank)
+    peak64 = _lib.fp64_peak(local_rank)
+    d2h_peak = _lib.d2h_peak(local_rank, max(frame_bytes // max(world, 1), 1 << 20))
 
     # warm-up through the full end-to-end path
     for i in range(max(args.warmup, 0)):
@@ -331,15 +333,30 @@ def gpu_arm(args, rank, world, local_rank):
     split = {"path_ms": 0.0, "shadow_ms": 0.0, "other_ms": 0.0, "path_launches": 0, "shadow_launches": 0}
     for i in range(args.steps):
         _lib.l2_flush(local_rank)
-        # per-launch CUDA events (two per kernel on the launching stream) split the frame by kernel class
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(i), **common)
+        dev.wait(0)
+        st = dev.stats(0)
+        kernel_ms += st["kernel_ms"]                  # two CUDA events on the launching stream around the frame's launches
+        rays += st["rays"]
+        launches += st["gpu_launches"]
+    barrier()
+    # split by kernel class: a separate pass with one event before and after EVERY launch (ERT_FLAG_TIME_KERNELS;
+    # the events cost ~3 % on a 2 ms part, so the pass is kept out of `value`)
+    split_steps = max(1, min(args.steps, 5))
+    split_ms = 0.0
+    for i in range(split_steps):
+        _lib.l2_flush(local_rank)
         dev.render_async(w, h, depth, slot=0, camera=camera_for(i), flags=_lib.FLAG_TIME_KERNELS, **common)
         dev.wait(0)
         st = dev.stats(0)
-        kernel_ms += st["kernel_ms"]
-        rays += st["rays"]
-        launches += st["gpu_launches"]
+        split_ms += st["kernel_ms"]
         for k in split:
             split[k] += st[k]
+    for k in ("path_ms", "shadow_ms", "other_ms"):
+        split[k] *= args.steps / split_steps          # per-class ms below are divided by args.steps
+    split["path_launches"] = split["path_launches"] * args.steps // split_steps
+    split["shadow_launches"] = split["shadow_launches"] * args.steps // split_steps
+    split_frame_ms = split_ms / split_steps
     barrier()
     kernel_ms_max = reduce(kernel_ms, "max")
     rays_all = reduce(rays, "sum")
@@ -422,8 +439,8 @@ def gpu_arm(args, rank, world, local_rank):
             "frac": sc_counted["path_filter_tests"] * 10 / max(p_s, 1e-12) / peak,
             "shadow_achieved": sc_counted["shadow_filter_tests"] * 10 / max(s_s, 1e-12) / 1e9,
             "shadow_frac": sc_counted["shadow_filter_tests"] * 10 / max(s_s, 1e-12) / peak,
-            "shadow_note": "shadow rays stop at their first occluder; their lanes idle until the segment ends, and "
-                           "only the tests up to the occluder are counted",
+            "shadow_note": "a shadow ray is a full nearest-object scan from the light (erl:256-267 calls "
+                           "nearest_object_intersecting_ray/2): every shadow ray meets every sphere, as in the reference",
         }
     e2e_wall_max = reduce(e2e_wall, "max")
     e2e_dev_ms_max = reduce(e2e_dev_ms, "max")
@@ -432,9 +449,13 @@ def gpu_arm(args, rank, world, local_rank):
 
     # the assembled host frame must equal a single-GPU render of the whole frame
     assembled_ok = None
-    if world > 1 and rank == 0 and args.workload != "c5":
-        full, _ = dev.render(w, h, depth, fmt=fmt, accel=accel)
-        assembled_ok = bool(np.array_equal(full, shared.array(np.uint8, (h, w, 3))))
+    if world > 1:
+        dev.render_async(w, h, depth, slot=0, camera=camera_for(0), host_ptr=hosts[0].ptr, host_bytes=frame_bytes, **common)
+        dev.wait(0)
+        barrier()
+        if rank == 0:
+            full, _ = dev.render(w, h, depth, fmt=fmt, accel=accel, camera=camera_for(0))
+            assembled_ok = bool(np.array_equal(full, shared.array(np.uint8, (h, w, 3))))
 
     if rank == 0:
         steps = max(args.steps, 1)
@@ -456,13 +477,69 @@ def gpu_arm(args, rank, world, local_rank):
         else:
             lane_instr, dom_s = frame_lane_instr, k_s
         achieved = lane_instr / dom_s
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload)
-            except Exception:
-                traffic = None
+        exact_kernel = (not wavefront) and counted["accel_used"] == "exact"
+        if exact_kernel:
+            # small scenes: every (ray, object) is decided in the literal FP64 arithmetic; the kernel is bound by the
+            # FP64 pipe (and, at this size, by launch latency), not by FP32 filters
+            fp64_instr = counted["exact_sphere_tests"] * 20 + counted["exact_other_tests"] * 30
+            roof = {
+                "bound": "fp64", "achieved": fp64_instr / k_s / 1e9, "peak": peak64 / 1e9, "unit": "Glane-instr/s",
+                "frac": fp64_instr / k_s / peak64, "traffic": None,
+                "kernel": "render_free_kernel<EXACT>",
+                "accounting": "20 FP64 instructions per ray/sphere literal test on its reject path (erl:364-378: 5 DADD/DSUB "
+                              "for O-C and the sums, 15 DMUL/DADD for b, c and the discriminant) + 30 per ray/plane or "
+                              "ray/triangle test, counted by an instrumented run of the same frame, divided by the frame's "
+                              "CUDA-event time; hits add two square roots and two divisions that are not counted",
+                "peak_source": "in-bench register-resident DFMA loop on this GPU",
+                "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
+                "exact_fp64_other_tests": int(counted["exact_other_tests"]),
+                "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
+                "note": "SURVEY 8(d) calls C2/C5 framebuffer-bound: that holds end to end (see e2e.roofline, the D2H copy); "
+                        "the kernel itself writes 3 B/pixel and is nowhere near HBM",
+            }
+        else:
+            roof = {
+                "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": ({("bvh", "path"): "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
+                            ("bvh", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
+                            ("grid", "path"): "wf_trace_path<GRID> + wf_trace_path_refill<GRID> (cell-grid walks of the path rays, all bounces)",
+                            ("grid", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
+                            ("linear", "path"): "wf_scan<path> (brute-force filter scan of the path rays)",
+                            ("linear", "shadow"): "wf_scan<shadow> (brute-force filter scan of the shadow rays)"}
+                           .get((counted["accel_used"], dom), "?") if wavefront else
+                           {"bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel"}.get(counted["accel_used"], "?")),
+                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test + 4 per "
+                              "cell step (FFMA, FADD, two FMNMX) of the named kernels (counts from an instrumented run of the same frame on rank 0), divided "
+                              "by their CUDA-event time in a separate pass of %d frames with one event before and after every "
+                              "launch (ERT_FLAG_TIME_KERNELS; `value` is timed without those events)" % split_steps,
+                "launches_per_step": (split[dom + "_launches"] / steps) if wavefront else 1,
+                "avg_launch_ms": (split[dom + "_ms"] / max(split[dom + "_launches"], 1)) if wavefront else kernel_ms / steps,
+                "share_of_step": (split[dom + "_ms"] / steps / split_frame_ms) if wavefront else 1.0,
+                "box_tests": int(counted[dom + "_box_tests"] if wavefront else counted["box_tests"]),
+                "sphere_filter_tests": int(counted[dom + "_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
+                "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
+                "cell_steps": int(counted.get("cell_steps", 0)),
+                "frame": {"lane_instr": int(frame_lane_instr), "frac": frame_lane_instr / k_s / peak,
+                          "box_tests": int(counted["box_tests"]),
+                          "sphere_filter_tests": int(counted["sphere_filter_tests"]),
+                          "class_frac": {c: ((counted[c + "_box_tests"] * 6 + counted[c + "_filter_tests"] * 10
+                                              + (cell_instr if c == "path" else 0))
+                                             / max(split[c + "_ms"] / steps * 1e-3, 1e-12) / peak)
+                                         for c in ("path", "shadow")} if wavefront else None,
+                          "ms": {"path": split["path_ms"] / steps, "shadow": split["shadow_ms"] / steps,
+                                 "other": split["other_ms"] / steps, "all_with_per_launch_events": split_frame_ms,
+                                 "all": kernel_ms / steps}},
+                "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry); "
+                               "FFMA with an immediate addend, the fastest form",
+                "peak_rrr": peak_rrr / 1e9, "frac_of_peak_rrr": achieved / peak_rrr,
+                "peak_rrr_source": "the same loop with three register operands per FFMA, the form the intersection "
+                                   "kernels issue",
+                "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
+                "traffic_note": "dram__bytes of the named kernels are in the ncu summaries under profiles/ (r02_*_full.txt); "
+                                "bench.py does not run under ncu and reports no number it did not measure",
+            }
+        d2h_per_gpu = (d2h_all / max(world, 1) / steps) / max(e2e_ms * 1e-3, 1e-12) / 1e9
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -476,6 +553,8 @@ def gpu_arm(args, rank, world, local_rank):
                 "partition": ("row bands of %d rows dealt round-robin to %d GPUs" % (band_rows, world)
                               if world > 1 else "whole frame on one GPU"),
                 "l2": "flushed between steps (256 MiB device write outside the timed events)",
+                "timing": "value: CUDA events around the frame's launches on the launching stream, no per-launch events; "
+                          "max over ranks of the per-rank sums",
                 "output": "RGB8 framebuffer (min(trunc(C*255),255) fused)",
                 "scene_upload_s": t_upload,
             },
@@ -488,7 +567,14 @@ def gpu_arm(args, rank, world, local_rank):
                              "params in, kernel, pinned D2H of the RGB8 rows; L2 not flushed in this loop (the only "
                              "per-step data is the output frame)") if pipelined else
                             "ert_render() per step: camera + params in, kernel, pinned D2H of the RGB8 rows",
-                    "frames_per_s": 1e3 / e2e_ms},
+                    "frames_per_s": 1e3 / e2e_ms,
+                    "d2h_gbs_per_gpu": d2h_per_gpu,
+                    "roofline": {"bound": "pcie", "achieved": d2h_per_gpu, "peak": d2h_peak, "unit": "GB/s per GPU",
+                                 "frac": d2h_per_gpu / max(d2h_peak, 1e-12),
+                                 "peak_source": "in-bench cudaMemcpyAsync device -> pinned host of one part's bytes on this "
+                                                "GPU, alone on the box",
+                                 "note": "meaningful for the frames whose step is the copy (C2, C5); on C3/C4 the copy is "
+                                         "a few percent of the step"}},
             "gpu_launches": launches_all,
             "reference_equivalent": {
                 "ratio": refeq_ratio, "rays_per_frame": refeq_ratio * rays_all / steps,
@@ -496,44 +582,7 @@ def gpu_arm(args, rank, world, local_rank):
                 "what": "rays the reference would trace for the same frame: its lighting function re-traces the "
                         "reflection once per light (erl:216-224), so level b runs L^b times; from the per-level "
                         "counts of rank 0's part (ert_stats.bounce_path_rays / bounce_hits)"},
-            "roofline": {
-                "bound": "fp32", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Glane-instr/s",
-                "frac": achieved / peak, "traffic": traffic,
-                "kernel": ({("bvh", "path"): "wf_trace_path + wf_trace_path_refill (BVH walks of the path rays, all bounces)",
-                            ("bvh", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
-                            ("grid", "path"): "wf_trace_path<GRID> + wf_trace_path_refill<GRID> (cell-grid walks of the path rays, all bounces)",
-                            ("grid", "shadow"): "wf_trace_shadow (direction grids / BVH walks of the shadow rays)",
-                            ("linear", "path"): "wf_scan_path (brute-force filter scan of the path rays)",
-                            ("linear", "shadow"): "wf_scan_shadow (brute-force filter scan of the shadow rays)"}
-                           .get((counted["accel_used"], dom), "?") if wavefront else
-                           {"bvh_mega": "render_free_kernel<BVH>", "linear": "render_tiled_kernel",
-                            "exact": "render_free_kernel<EXACT>"}.get(counted["accel_used"], "?")),
-                "accounting": "6 FFMA per ray/AABB slab test + 10 FP32-pipe instr per ray/sphere filter test + 4 per "
-                              "cell step (FFMA, FADD, two FMNMX) of the named kernels (counts from an instrumented run of the same frame on rank 0), divided "
-                              "by their CUDA-event time inside the timed steps",
-                "launches_per_step": (split[dom + "_launches"] / steps) if wavefront else 1,
-                "avg_launch_ms": (split[dom + "_ms"] / max(split[dom + "_launches"], 1)) if wavefront else kernel_ms / steps,
-                "share_of_step": (split[dom + "_ms"] / kernel_ms) if wavefront else 1.0,
-                "box_tests": int(counted[dom + "_box_tests"] if wavefront else counted["box_tests"]),
-                "sphere_filter_tests": int(counted[dom + "_filter_tests"] if wavefront else counted["sphere_filter_tests"]),
-                "exact_fp64_sphere_tests": int(counted["exact_sphere_tests"]),
-                "cell_steps": int(counted.get("cell_steps", 0)),
-                "frame": {"lane_instr": int(frame_lane_instr), "frac": frame_lane_instr / k_s / peak,
-                          "box_tests": int(counted["box_tests"]),
-                          "sphere_filter_tests": int(counted["sphere_filter_tests"]),
-                          "class_frac": {c: ((counted[c + "_box_tests"] * 6 + counted[c + "_filter_tests"] * 10
-                                              + (cell_instr if c == "path" else 0))
-                                             / max(split[c + "_ms"] / steps * 1e-3, 1e-12) / peak)
-                                         for c in ("path", "shadow")} if wavefront else None,
-                          "ms": {"path": split["path_ms"] / steps, "shadow": split["shadow_ms"] / steps,
-                                 "other": split["other_ms"] / steps, "all": kernel_ms / steps}},
-                "peak_source": "in-bench register-resident FFMA loop on this GPU (MEASURED_PEAKS.json has no FP32 entry); "
-                               "FFMA with an immediate addend, the fastest form",
-                "peak_rrr": peak_rrr / 1e9, "frac_of_peak_rrr": achieved / peak_rrr,
-                "peak_rrr_source": "the same loop with three register operands per FFMA, the form the intersection "
-                                   "kernels issue",
-                "framebuffer_gbs": (w * h * 3 / world) / k_s / 1e9,
-            },
+            "roofline": roof,
         }
         if scan is not None:
             line["roofline_scan"] = scan

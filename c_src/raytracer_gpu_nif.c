@@ -3,7 +3,7 @@
  *
  * Glue only: Erlang term -> ert_scene_desc / ert_render_params -> ert_* call ->
  * Erlang term.  All logic lives behind ert_b200.h.  Every NIF that touches the
- * GPU is a dirty CPU-bound NIF (a 4K frame blocks for milliseconds to seconds).
+ * GPU runs on a dirty scheduler (a 4K frame blocks for milliseconds to seconds).
  * No ports, no CPU fallback: errors come back as {error, {Class, Code, Msg}}
  * and undecodable terms raise badarg.
  *
@@ -30,10 +30,19 @@
 #include "ert_b200.h"
 
 static ErlNifResourceType *scene_rt;
+static ErlNifResourceType *frame_rt;
 
 typedef struct {
     ert_scene *scene;
 } scene_res;
+
+/* A frame in page-locked host memory (ert_host_alloc): the GPUs copy their rows straight into it, and Erlang
+ * sees it as a binary without another copy (enif_make_resource_binary keeps this resource alive). */
+typedef struct {
+    void *pinned;
+    size_t bytes;
+    int width, height, format;
+} frame_res;
 
 static void scene_dtor(ErlNifEnv *env, void *obj)
 {
@@ -43,17 +52,32 @@ static void scene_dtor(ErlNifEnv *env, void *obj)
     r->scene = NULL;
 }
 
+static void frame_dtor(ErlNifEnv *env, void *obj)
+{
+    frame_res *r = (frame_res *)obj;
+    (void)env;
+    if (r->pinned) ert_host_free(r->pinned);
+    r->pinned = NULL;
+}
+
+static int open_types(ErlNifEnv *env, ErlNifResourceFlags flags)
+{
+    scene_rt = enif_open_resource_type(env, NULL, "ert_b200_scene", scene_dtor, flags, NULL);
+    frame_rt = enif_open_resource_type(env, NULL, "ert_b200_frame", frame_dtor, flags, NULL);
+    return scene_rt && frame_rt ? 0 : 1;
+}
+
 static int load(ErlNifEnv *env, void **priv, ERL_NIF_TERM info)
 {
     (void)priv; (void)info;
-    scene_rt = enif_open_resource_type(env, NULL, "ert_b200_scene", scene_dtor, ERL_NIF_RT_CREATE, NULL);
-    return scene_rt ? 0 : 1;
+    return open_types(env, ERL_NIF_RT_CREATE);
 }
 
+/* hot code upgrade: the resource types exist already and are taken over by the new module instance */
 static int upgrade(ErlNifEnv *env, void **priv, void **old_priv, ERL_NIF_TERM info)
 {
-    (void)old_priv;
-    return load(env, priv, info);
+    (void)priv; (void)old_priv; (void)info;
+    return open_types(env, (ErlNifResourceFlags)(ERL_NIF_RT_CREATE | ERL_NIF_RT_TAKEOVER));
 }
 
 /* ---- term helpers --------------------------------------------------------- */
@@ -127,10 +151,25 @@ static int decode_scene(ErlNifEnv *env, ERL_NIF_TERM list, decoded_scene *d)
     memset(d, 0, sizeof *d);
     if (!enif_get_list_length(env, list, &len) || len == 0) return 0;
     if (!enif_get_list_cell(env, list, &head, &tail) || !get_camera(env, head, &d->desc.camera)) return 0;
-    d->lights = calloc(len, sizeof *d->lights);
-    d->spheres = calloc(len, sizeof *d->spheres);
-    d->triangles = calloc(len, sizeof *d->triangles);
-    d->planes = calloc(len, sizeof *d->planes);
+    {
+        /* first pass: how many records of each kind (by tag and arity), so that every table is allocated at its
+         * size — a 1 M-sphere list would otherwise pay for four full-length tables */
+        size_t nl = 0, ns = 0, nt = 0, np = 0;
+        ERL_NIF_TERM h2, t2 = tail;
+        while (enif_get_list_cell(env, t2, &h2, &t2)) {
+            int arity;
+            const ERL_NIF_TERM *e;
+            if (!enif_get_tuple(env, h2, &arity, &e) || arity < 1) continue;
+            if (arity == 4 && is_atom_named(env, e[0], "point_light")) nl++;
+            else if (arity == 4 && is_atom_named(env, e[0], "sphere")) ns++;
+            else if (arity == 5 && is_atom_named(env, e[0], "triangle")) nt++;
+            else if (arity == 4 && is_atom_named(env, e[0], "plane")) np++;
+        }
+        d->lights = calloc(nl ? nl : 1, sizeof *d->lights);
+        d->spheres = calloc(ns ? ns : 1, sizeof *d->spheres);
+        d->triangles = calloc(nt ? nt : 1, sizeof *d->triangles);
+        d->planes = calloc(np ? np : 1, sizeof *d->planes);
+    }
     if (!d->lights || !d->spheres || !d->triangles || !d->planes) { decoded_free(d); return 0; }
     while (enif_get_list_cell(env, tail, &head, &tail)) {
         int arity;
@@ -235,6 +274,29 @@ static ERL_NIF_TERM nif_scene_upload(ErlNifEnv *env, int argc, const ERL_NIF_TER
     return enif_make_tuple2(env, enif_make_atom(env, "ok"), term);
 }
 
+/* scene_clone(Handle, Device) -> {ok, Handle2} | {error, _}   (dirty)
+ * The flattened scene and its acceleration structures are copied to another GPU without rebuilding them
+ * (ert_scene_clone): one upload + N-1 clones instead of N uploads of the same term. */
+static ERL_NIF_TERM nif_scene_clone(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
+{
+    scene_res *src, *res;
+    ert_scene *scene = NULL;
+    ERL_NIF_TERM term;
+    int device, rc;
+    (void)argc;
+    if (!enif_get_resource(env, argv[0], scene_rt, (void **)&src) || !src->scene) return enif_make_badarg(env);
+    if (!enif_get_int(env, argv[1], &device)) return enif_make_badarg(env);
+    rc = ert_scene_clone(src->scene, device, &scene);
+    if (rc == ERT_ERR_BADARG) return enif_make_badarg(env);
+    if (rc != ERT_OK) return make_error(env, rc);
+    res = enif_alloc_resource(scene_rt, sizeof *res);
+    if (!res) { ert_scene_destroy(scene); return make_error(env, ERT_ERR_NOMEM); }
+    res->scene = scene;
+    term = enif_make_resource(env, res);
+    enif_release_resource(res);
+    return enif_make_tuple2(env, enif_make_atom(env, "ok"), term);
+}
+
 /* Opts: proplist of {format, rgb8|f32|f64} | {accel, auto|exact|linear|bvh|bvh_mega|grid} |
  *       {part, {BandRows, NParts, Part}} | {camera, CameraRecord} */
 static int decode_opts(ErlNifEnv *env, ERL_NIF_TERM opts, ert_render_params *p, ert_camera *cam)
@@ -290,28 +352,100 @@ static int decode_render_args(ErlNifEnv *env, const ERL_NIF_TERM argv[], scene_r
     return decode_opts(env, argv[4], p, cam);
 }
 
+static frame_res *frame_new(int width, int height, int format)
+{
+    frame_res *fr = enif_alloc_resource(frame_rt, sizeof *fr);
+    if (!fr) return NULL;
+    fr->pinned = NULL;
+    fr->width = width; fr->height = height; fr->format = format;
+    fr->bytes = (size_t)width * (size_t)height * 3 * elem_size(format);
+    if (ert_host_alloc(fr->bytes, &fr->pinned) != ERT_OK) {
+        enif_release_resource(fr);             /* runs frame_dtor with pinned == NULL */
+        return NULL;
+    }
+    memset(fr->pinned, 0, fr->bytes);
+    return fr;
+}
+
 /* render(Handle, Width, Height, Depth, Opts) -> {ok, FrameBinary} | {error, _}   (dirty)
- * The binary is the full row-major frame (Y = 0 first), 3 channels per pixel. */
+ * The binary is the full row-major frame (Y = 0 first), 3 channels per pixel.  It is a resource binary over
+ * page-locked memory: the rows arrive by asynchronous D2H copies and Erlang gets them without a further copy. */
 static ERL_NIF_TERM nif_render(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
 {
     scene_res *res;
     ert_render_params p;
     ert_camera cam;
+    frame_res *fr;
     ERL_NIF_TERM bin;
-    unsigned char *buf;
-    size_t bytes;
     int rc;
     (void)argc;
     if (!decode_render_args(env, argv, &res, &p, &cam)) return enif_make_badarg(env);
     if (p.width <= 0 || p.height <= 0 || p.depth < 0) return enif_make_badarg(env);   /* guards erl:89 */
-    bytes = (size_t)p.width * (size_t)p.height * 3 * elem_size(p.format);
-    buf = enif_make_new_binary(env, bytes, &bin);
-    if (!buf) return make_error(env, ERT_ERR_NOMEM);
-    memset(buf, 0, bytes);
-    rc = ert_render(res->scene, &p, buf, bytes);
+    fr = frame_new(p.width, p.height, p.format);
+    if (!fr) return make_error(env, ERT_ERR_NOMEM);
+    rc = ert_render(res->scene, &p, fr->pinned, fr->bytes);
+    if (rc != ERT_OK) {
+        enif_release_resource(fr);
+        return rc == ERT_ERR_BADARG ? enif_make_badarg(env) : make_error(env, rc);
+    }
+    bin = enif_make_resource_binary(env, fr, fr->pinned, fr->bytes);
+    enif_release_resource(fr);                 /* the binary term holds the remaining reference */
+    return enif_make_tuple2(env, enif_make_atom(env, "ok"), bin);
+}
+
+/* frame_alloc(Width, Height, Format) -> {ok, Frame} | {error, _}
+ * One page-locked frame that several renders (one per GPU, each with its {part, ...} option) fill in place. */
+static ERL_NIF_TERM nif_frame_alloc(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
+{
+    int w, h, format;
+    frame_res *fr;
+    ERL_NIF_TERM term;
+    (void)argc;
+    if (!enif_get_int(env, argv[0], &w) || !enif_get_int(env, argv[1], &h) || w <= 0 || h <= 0) return enif_make_badarg(env);
+    if (is_atom_named(env, argv[2], "rgb8")) format = ERT_FMT_RGB8;
+    else if (is_atom_named(env, argv[2], "f32")) format = ERT_FMT_F32;
+    else if (is_atom_named(env, argv[2], "f64")) format = ERT_FMT_F64;
+    else return enif_make_badarg(env);
+    fr = frame_new(w, h, format);
+    if (!fr) return make_error(env, ERT_ERR_NOMEM);
+    term = enif_make_resource(env, fr);
+    enif_release_resource(fr);
+    return enif_make_tuple2(env, enif_make_atom(env, "ok"), term);
+}
+
+/* render_into(Handle, Frame, Depth, Opts) -> ok | {error, _}   (dirty)
+ * Renders this call's part ({part, {BandRows, NParts, Part}}) of the frame's size and format; its rows land at
+ * their place in Frame.  Calls for different parts may run at the same time from different processes. */
+static ERL_NIF_TERM nif_render_into(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
+{
+    scene_res *res;
+    frame_res *fr;
+    ert_render_params p;
+    ert_camera cam;
+    int rc;
+    (void)argc;
+    memset(&p, 0, sizeof p);
+    if (!enif_get_resource(env, argv[0], scene_rt, (void **)&res) || !res->scene) return enif_make_badarg(env);
+    if (!enif_get_resource(env, argv[1], frame_rt, (void **)&fr) || !fr->pinned) return enif_make_badarg(env);
+    if (!enif_get_int(env, argv[2], &p.depth) || p.depth < 0) return enif_make_badarg(env);
+    p.width = fr->width; p.height = fr->height;
+    p.format = fr->format;
+    p.accel = ERT_ACCEL_AUTO;
+    p.n_parts = 1;
+    if (!decode_opts(env, argv[3], &p, &cam) || p.format != fr->format) return enif_make_badarg(env);
+    rc = ert_render(res->scene, &p, fr->pinned, fr->bytes);
     if (rc == ERT_ERR_BADARG) return enif_make_badarg(env);
     if (rc != ERT_OK) return make_error(env, rc);
-    return enif_make_tuple2(env, enif_make_atom(env, "ok"), bin);
+    return enif_make_atom(env, "ok");
+}
+
+/* frame_binary(Frame) -> Binary: the frame's memory as a binary, no copy */
+static ERL_NIF_TERM nif_frame_binary(ErlNifEnv *env, int argc, const ERL_NIF_TERM argv[])
+{
+    frame_res *fr;
+    (void)argc;
+    if (!enif_get_resource(env, argv[0], frame_rt, (void **)&fr) || !fr->pinned) return enif_make_badarg(env);
+    return enif_make_resource_binary(env, fr, fr->pinned, fr->bytes);
 }
 
 /* render_pixel_list(Handle, Width, Height, Depth, Opts) -> [{Index, {R,G,B}}] | {error, _}   (dirty)
@@ -340,6 +474,18 @@ static ERL_NIF_TERM nif_render_pixel_list(ErlNifEnv *env, int argc, const ERL_NI
         free(buf);
         return rc == ERT_ERR_BADARG ? enif_make_badarg(env) : make_error(env, rc);
     }
+    {
+        /* BEAM floats are finite (an overflow is badarith in the reference): a non-finite channel cannot be a term */
+        size_t k;
+        for (k = 0; k < 3 * n; k++) {
+            if (!(buf[k] - buf[k] == 0.0)) {
+                free(buf);
+                return enif_make_tuple2(env, enif_make_atom(env, "error"),
+                                        enif_make_tuple2(env, enif_make_atom(env, "badarith"),
+                                                         enif_make_int64(env, (ErlNifSInt64)(k / 3))));
+            }
+        }
+    }
     list = enif_make_list(env, 0);
     while (n-- > 0) {
         ERL_NIF_TERM px = enif_make_tuple3(env, enif_make_double(env, buf[3 * n]), enif_make_double(env, buf[3 * n + 1]),
@@ -353,9 +499,14 @@ static ERL_NIF_TERM nif_render_pixel_list(ErlNifEnv *env, int argc, const ERL_NI
 static ErlNifFunc nif_funcs[] = {
     {"device_count", 0, nif_device_count, 0},
     {"scene_info", 1, nif_scene_info, 0},
+    /* scene_upload builds the BVH and the grids on the host: CPU-bound; the others wait for the GPU: IO-bound */
     {"scene_upload", 2, nif_scene_upload, ERL_NIF_DIRTY_JOB_CPU_BOUND},
-    {"render", 5, nif_render, ERL_NIF_DIRTY_JOB_CPU_BOUND},
-    {"render_pixel_list", 5, nif_render_pixel_list, ERL_NIF_DIRTY_JOB_CPU_BOUND},
+    {"scene_clone", 2, nif_scene_clone, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"render", 5, nif_render, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"render_pixel_list", 5, nif_render_pixel_list, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"frame_alloc", 3, nif_frame_alloc, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"render_into", 4, nif_render_into, ERL_NIF_DIRTY_JOB_IO_BOUND},
+    {"frame_binary", 1, nif_frame_binary, 0},
 };
 
 ERL_NIF_INIT(raytracer_gpu, nif_funcs, load, NULL, upgrade, NULL)

@@ -101,7 +101,7 @@ EXPORTS = [
     "ert_abi_version", "ert_last_error", "ert_device_count", "ert_scene_create", "ert_scene_clone",
     "ert_scene_destroy", "ert_render", "ert_render_async", "ert_wait", "ert_download",
     "ert_get_stats", "ert_trace_rays", "ert_host_alloc", "ert_host_free", "ert_host_register",
-    "ert_host_unregister", "ert_fp32_peak", "ert_fp32_peak_rrr", "ert_l2_flush",
+    "ert_host_unregister", "ert_fp32_peak", "ert_fp32_peak_rrr", "ert_fp64_peak", "ert_d2h_peak", "ert_l2_flush",
 ]
 
 _lib = None
@@ -137,6 +137,8 @@ def load():
     L.ert_host_unregister.argtypes = [vp]
     L.ert_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     L.ert_fp32_peak_rrr.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.ert_fp64_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    L.ert_d2h_peak.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double)]
     L.ert_l2_flush.argtypes = [ctypes.c_int]
     for name in EXPORTS:
         if name not in ("ert_last_error",):
@@ -280,6 +282,18 @@ def fp32_peak(device=0):
 def fp32_peak_rrr(device=0):
     v = ctypes.c_double(0)
     check(load().ert_fp32_peak_rrr(int(device), ctypes.byref(v)))
+    return v.value
+
+
+def fp64_peak(device=0):
+    v = ctypes.c_double(0)
+    check(load().ert_fp64_peak(int(device), ctypes.byref(v)))
+    return v.value
+
+
+def d2h_peak(device=0, nbytes=256 << 20):
+    v = ctypes.c_double(0)
+    check(load().ert_d2h_peak(int(device), int(nbytes), ctypes.byref(v)))
     return v.value
 
 

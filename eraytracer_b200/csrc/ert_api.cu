@@ -1249,6 +1249,78 @@ int ert_fp32_peak_rrr(int device, double *lane_instr_per_s)
     return ERT_OK;
 }
 
+int ert_fp64_peak(int device, double *lane_instr_per_s)
+{
+    if (!lane_instr_per_s) return fail(ERT_ERR_BADARG, "out is NULL");
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    int blocks = prop.multiProcessorCount * 8;
+    double *out = nullptr, *in = nullptr;
+    CU(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)));
+    CU(cudaMalloc(&in, 8 * sizeof(double)));
+    const double host_in[8] = {1.0, 0.9999, 0.99991, 0.0001, 0.00011, 0, 0, 0};
+    CU(cudaMemcpy(in, host_in, sizeof host_in, cudaMemcpyHostToDevice));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const int iters = 2048;
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(a));
+        fp64_peak_kernel<<<blocks, 256>>>(out, iters, in);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double rate = (double)blocks * 256.0 * iters * kPeakFfmaPerIter / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, rate);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    cudaFree(in);
+    *lane_instr_per_s = best;
+    return ERT_OK;
+}
+
+int ert_d2h_peak(int device, size_t bytes, double *gb_per_s)
+{
+    if (!gb_per_s) return fail(ERT_ERR_BADARG, "out is NULL");
+    int rc;
+    if ((rc = check_device(device)) != ERT_OK) return rc;
+    CU(cudaSetDevice(device));
+    bytes = std::max<size_t>(bytes, 1 << 20);
+    void *dev = nullptr, *host = nullptr;
+    CU(cudaMalloc(&dev, bytes));
+    if (cudaMallocHost(&host, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(dev);
+        return fail(ERT_ERR_NOMEM, "out of pinned host memory");
+    }
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(a));
+        CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, 0));
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::max(best, (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFreeHost(host);
+    cudaFree(dev);
+    *gb_per_s = best;
+    return ERT_OK;
+}
+
 int ert_l2_flush(int device)
 {
     int rc;

@@ -940,6 +940,24 @@ __global__ void __launch_bounds__(256) fp32_peak_rrr_kernel(float *out, int iter
     if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 counterpart (the literal tests of the small-scene kernels are DADD/DMUL/DFMA chains)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, const double *__restrict__ in)
+{
+    double a0 = in[0] + threadIdx.x, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3.;
+    double a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m0 = in[1], m1 = in[2], c0 = in[3], c1 = in[4];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            a0 = __fma_rn(a0, m0, c0); a1 = __fma_rn(a1, m1, c1); a2 = __fma_rn(a2, m0, c1); a3 = __fma_rn(a3, m1, c0);
+            a4 = __fma_rn(a4, m0, c0); a5 = __fma_rn(a5, m1, c1); a6 = __fma_rn(a6, m0, c1); a7 = __fma_rn(a7, m1, c0);
+        }
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void l2_flush_kernel(uint4 *buf, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

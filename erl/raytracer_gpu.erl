@@ -16,7 +16,8 @@
          raytraced_pixel_list_gpu_distributed/4,
          render_binary/5,
          write_binary_to_ppm/4,
-         device_count/0, scene_info/1, scene_upload/2, render/5, render_pixel_list/5]).
+         device_count/0, scene_info/1, scene_upload/2, scene_clone/2, render/5, render_pixel_list/5,
+         frame_alloc/3, render_into/4, frame_binary/1]).
 -on_load(init/0).
 
 init() ->
@@ -30,6 +31,10 @@ init() ->
 device_count() -> erlang:nif_error(nif_not_loaded).
 scene_info(_Scene) -> erlang:nif_error(nif_not_loaded).
 scene_upload(_Scene, _Device) -> erlang:nif_error(nif_not_loaded).
+scene_clone(_Handle, _Device) -> erlang:nif_error(nif_not_loaded).
+frame_alloc(_Width, _Height, _Format) -> erlang:nif_error(nif_not_loaded).
+render_into(_Handle, _Frame, _Depth, _Opts) -> erlang:nif_error(nif_not_loaded).
+frame_binary(_Frame) -> erlang:nif_error(nif_not_loaded).
 render(_Handle, _Width, _Height, _Depth, _Opts) -> erlang:nif_error(nif_not_loaded).
 render_pixel_list(_Handle, _Width, _Height, _Depth, _Opts) -> erlang:nif_error(nif_not_loaded).
 
@@ -46,9 +51,8 @@ raytraced_pixel_list_gpu(Width, Height, Scene, Recursion_depth)
     end.
 
 %% Row bands dealt round-robin to every GPU of the box; one Erlang process per GPU calls
-%% the dirty NIF, each returns the full-size frame with only its rows filled, and the
-%% rows are stitched by binary part copies (the role of distribute_work/7 + master/3,
-%% raytracer.erl:139-161, without one message per pixel).
+%% the dirty NIF and its GPU fills its rows of ONE shared frame (the role of
+%% distribute_work/7 + master/3, raytracer.erl:139-161, without one message per pixel).
 raytraced_pixel_list_gpu_distributed(0, 0, _, _) ->
     done;
 raytraced_pixel_list_gpu_distributed(Width, Height, Scene, Recursion_depth)
@@ -57,31 +61,26 @@ raytraced_pixel_list_gpu_distributed(Width, Height, Scene, Recursion_depth)
     pixel_list_from_f64(Frame, 0, []).
 
 %% Whole frame as a binary (rgb8 by default): the scalable return type.
+%% The scene term is decoded and its acceleration structures are built ONCE (scene_upload on device 0);
+%% the other GPUs get copies (scene_clone).  One page-locked frame is shared by all parts: every GPU copies
+%% its row bands to their place in it, and the result is that memory as a binary — no per-part frames and
+%% no stitching on the Erlang side.
 render_binary(Width, Height, Scene, Recursion_depth, Opts) when Width > 0, Height > 0 ->
     {ok, N} = ok_or_exit(device_count()),
+    Format = proplists:get_value(format, Opts, rgb8),
+    {ok, H0} = ok_or_exit(scene_upload(Scene, 0)),
+    Handles = [H0 | [begin {ok, H} = ok_or_exit(scene_clone(H0, Dev)), H end || Dev <- lists:seq(1, N - 1)]],
+    {ok, Frame} = ok_or_exit(frame_alloc(Width, Height, Format)),
     BandRows = 8,
     Parent = self(),
     Pids = [spawn_link(fun() ->
-                {ok, H} = ok_or_exit(scene_upload(Scene, Dev)),
-                Parent ! {self(), render(H, Width, Height, Recursion_depth,
-                                         [{part, {BandRows, N, Dev}} | Opts])}
-            end) || Dev <- lists:seq(0, N - 1)],
-    Frames = [receive {Pid, {ok, Bin}} -> Bin;
-                      {Pid, {error, Reason}} -> exit({raytracer_gpu, Reason})
-              end || Pid <- Pids],
-    stitch(Frames, Width, Height, BandRows, proplists:get_value(format, Opts, rgb8)).
-
-stitch([Single], _W, _H, _BandRows, _Format) ->
-    Single;
-stitch(Frames, Width, Height, BandRows, Format) ->
-    RowBytes = Width * 3 * case Format of rgb8 -> 1; f32 -> 4; f64 -> 8 end,
-    N = length(Frames),
-    Bands = (Height + BandRows - 1) div BandRows,
-    iolist_to_binary(
-      [begin
-           Rows = min(BandRows, Height - B * BandRows),
-           binary:part(lists:nth((B rem N) + 1, Frames), B * BandRows * RowBytes, Rows * RowBytes)
-       end || B <- lists:seq(0, Bands - 1)]).
+                Parent ! {self(), render_into(H, Frame, Recursion_depth,
+                                              [{part, {BandRows, N, Part}} | Opts])}
+            end) || {Part, H} <- lists:zip(lists:seq(0, N - 1), Handles)],
+    [receive {Pid, ok} -> ok;
+             {Pid, {error, Reason}} -> exit({raytracer_gpu, Reason})
+     end || Pid <- Pids],
+    frame_binary(Frame).
 
 pixel_list_from_f64(<<>>, _I, Acc) ->
     lists:reverse(Acc);

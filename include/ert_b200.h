@@ -238,6 +238,13 @@ ERT_API int ert_fp32_peak(int device, double *lane_instr_per_s);
 /* The same loop with three register operands per FFMA, the form the intersection kernels issue. */
 ERT_API int ert_fp32_peak_rrr(int device, double *lane_instr_per_s);
 
+/* Measured FP64 issue peak of `device` (register-resident DFMA loop): the roofline denominator of the kernels
+ * that decide every object in the literal FP64 arithmetic (small scenes, ERT_ACCEL_EXACT). */
+ERT_API int ert_fp64_peak(int device, double *lane_instr_per_s);
+/* Measured device -> pinned-host copy rate of `device` in GB/s for copies of `bytes` (the roofline denominator of
+ * the frames that are bound by getting the framebuffer to the host: C2, C5). */
+ERT_API int ert_d2h_peak(int device, size_t bytes, double *gb_per_s);
+
 /* Writes a buffer larger than L2 on `device` (bench hygiene between timed steps). */
 ERT_API int ert_l2_flush(int device);
 

@@ -6,6 +6,35 @@
  * NIF uses, with the real names and argument orders, backed by a tiny heap-term model
  * (mock_erl_nif.c), so that the NIF is compiled with -Wall -Werror and its term decode /
  * encode paths are executed by the test-suite.  It is not part of the product.
+ *
+ * Every prototype below restates the signature printed in the erl_nif(3) manual page of OTP 26
+ * (section "Exports"), from memory — nothing here was checked against an OTP installation:
+ *   int enif_is_atom(ErlNifEnv* env, ERL_NIF_TERM term)
+ *   int enif_is_empty_list(ErlNifEnv* env, ERL_NIF_TERM term)
+ *   int enif_get_atom(ErlNifEnv* env, ERL_NIF_TERM term, char* buf, unsigned size, ErlNifCharEncoding encode)
+ *   int enif_get_double(ErlNifEnv* env, ERL_NIF_TERM term, double* dp)          (fails on integers)
+ *   int enif_get_int(ErlNifEnv* env, ERL_NIF_TERM term, int* ip)
+ *   int enif_get_int64(ErlNifEnv* env, ERL_NIF_TERM term, ErlNifSInt64* ip)
+ *   int enif_get_tuple(ErlNifEnv* env, ERL_NIF_TERM term, int* arity, const ERL_NIF_TERM** array)
+ *   int enif_get_list_cell(ErlNifEnv* env, ERL_NIF_TERM list, ERL_NIF_TERM* head, ERL_NIF_TERM* tail)
+ *   int enif_get_list_length(ErlNifEnv* env, ERL_NIF_TERM term, unsigned* len)
+ *   ERL_NIF_TERM enif_make_atom(ErlNifEnv* env, const char* name)
+ *   ERL_NIF_TERM enif_make_int(ErlNifEnv* env, int i) / enif_make_int64(ErlNifEnv* env, ErlNifSInt64 i)
+ *   ERL_NIF_TERM enif_make_double(ErlNifEnv* env, double d)                     (d must be finite)
+ *   ERL_NIF_TERM enif_make_tuple(ErlNifEnv* env, unsigned cnt, ...) and the enif_make_tupleN macros
+ *   ERL_NIF_TERM enif_make_list(ErlNifEnv* env, unsigned cnt, ...) / enif_make_list_cell(env, head, tail)
+ *   ERL_NIF_TERM enif_make_string(ErlNifEnv* env, const char* string, ErlNifCharEncoding encoding)
+ *   unsigned char* enif_make_new_binary(ErlNifEnv* env, size_t size, ERL_NIF_TERM* termp)
+ *   ERL_NIF_TERM enif_make_badarg(ErlNifEnv* env)
+ *   ErlNifResourceType* enif_open_resource_type(ErlNifEnv* env, const char* module_str, const char* name,
+ *        ErlNifResourceDtor* dtor, ErlNifResourceFlags flags, ErlNifResourceFlags* tried)
+ *        (ERL_NIF_RT_CREATE alone fails when the type exists; upgrade passes CREATE | TAKEOVER)
+ *   void* enif_alloc_resource(ErlNifResourceType* type, unsigned size) / void enif_release_resource(void* obj)
+ *   ERL_NIF_TERM enif_make_resource(ErlNifEnv* env, void* obj)
+ *   int enif_get_resource(ErlNifEnv* env, ERL_NIF_TERM term, ErlNifResourceType* type, void** objp)
+ *   ERL_NIF_TERM enif_make_resource_binary(ErlNifEnv* env, void* obj, const void* data, size_t size)
+ *   ERL_NIF_INIT(MODULE, ErlNifFunc funcs[], load, NULL, upgrade, unload); ErlNifFunc = {name, arity, fptr, flags}
+ *        with flags 0, ERL_NIF_DIRTY_JOB_CPU_BOUND or ERL_NIF_DIRTY_JOB_IO_BOUND
  */
 #ifndef MOCK_ERL_NIF_H
 #define MOCK_ERL_NIF_H
@@ -77,6 +106,9 @@ void *enif_alloc_resource(ErlNifResourceType *, size_t size);
 void enif_release_resource(void *obj);
 ERL_NIF_TERM enif_make_resource(ErlNifEnv *, void *obj);
 int enif_get_resource(ErlNifEnv *, ERL_NIF_TERM, ErlNifResourceType *, void **objp);
+/* erl_nif(3): "ERL_NIF_TERM enif_make_resource_binary(ErlNifEnv* env, void* obj, const void* data, size_t size)" —
+ * a binary term whose bytes are `data`, owned by resource `obj`; the resource is kept until the binary is collected */
+ERL_NIF_TERM enif_make_resource_binary(ErlNifEnv *, void *obj, const void *data, size_t size);
 
 /* ---- mock-only helpers for the test harness (not in OTP) ----------------- */
 ErlNifEnv *mock_env_new(void);

@@ -19,6 +19,7 @@ typedef struct term {
         void *res;
         char *str;
     } u;
+    void *owner;            /* resource that owns a resource binary's bytes */
 } term;
 
 struct enif_environment_t { int unused; };
@@ -149,9 +150,24 @@ ERL_NIF_TERM enif_make_badarg(ErlNifEnv *e) { (void)e; return mk(T_BADARG); }
 ErlNifResourceType *enif_open_resource_type(ErlNifEnv *e, const char *m, const char *name, ErlNifResourceDtor *dtor,
                                             ErlNifResourceFlags flags, ErlNifResourceFlags *tried)
 {
-    ErlNifResourceType *rt = calloc(1, sizeof *rt);
-    (void)e; (void)m; (void)name; (void)flags;
+    /* like OTP: CREATE alone fails for a type that exists, TAKEOVER alone for one that does not */
+    static struct { char name[64]; ErlNifResourceType *rt; } known[8];
+    ErlNifResourceType *rt;
+    int k;
+    (void)e; (void)m;
+    for (k = 0; k < 8 && known[k].rt; k++) {
+        if (strcmp(known[k].name, name) == 0) {
+            if (!(flags & ERL_NIF_RT_TAKEOVER)) return NULL;
+            known[k].rt->dtor = dtor;
+            if (tried) *tried = ERL_NIF_RT_TAKEOVER;
+            return known[k].rt;
+        }
+    }
+    if (!(flags & ERL_NIF_RT_CREATE) || k == 8) return NULL;
+    rt = calloc(1, sizeof *rt);
     rt->dtor = dtor;
+    strncpy(known[k].name, name, sizeof known[k].name - 1);
+    known[k].rt = rt;
     if (tried) *tried = ERL_NIF_RT_CREATE;
     return rt;
 }
@@ -186,6 +202,17 @@ int enif_get_resource(ErlNifEnv *e, ERL_NIF_TERM t, ErlNifResourceType *type, vo
     *objp = T(t)->u.res;
     return 1;
 }
+ERL_NIF_TERM enif_make_resource_binary(ErlNifEnv *e, void *obj, const void *data, size_t size)
+{
+    /* the bytes stay where they are; the term holds a reference on the resource (dropped by mock_resource_gc) */
+    ERL_NIF_TERM t = mk(T_BIN);
+    (void)e;
+    ((res_hdr *)obj - 1)->refs++;
+    T(t)->u.bin.size = size;
+    T(t)->u.bin.data = (unsigned char *)data;
+    T(t)->owner = obj;
+    return t;
+}
 int mock_is_badarg(ERL_NIF_TERM t) { return T(t)->tag == T_BADARG; }
 int mock_is_binary(ERL_NIF_TERM t, const unsigned char **data, size_t *size)
 {
@@ -205,5 +232,10 @@ void mock_resource_gc(ERL_NIF_TERM t)
     if (T(t)->tag == T_RES && T(t)->u.res) {
         res_unref(T(t)->u.res);
         T(t)->u.res = NULL;
+    } else if (T(t)->tag == T_BIN && T(t)->owner) {
+        res_unref(T(t)->owner);
+        T(t)->owner = NULL;
+        T(t)->u.bin.data = NULL;
+        T(t)->u.bin.size = 0;
     }
 }

@@ -18,10 +18,29 @@ def beam():
 def test_nif_table(beam):
     assert beam.entry.name == b"raytracer_gpu"
     table = {k: f.flags for k, f in beam.funcs.items()}
-    assert set(table) == {("device_count", 0), ("scene_info", 1), ("scene_upload", 2), ("render", 5),
-                          ("render_pixel_list", 5)}
-    # everything that can block on the GPU runs on a dirty CPU scheduler
-    assert table[("scene_upload", 2)] == 1 and table[("render", 5)] == 1 and table[("render_pixel_list", 5)] == 1
+    assert set(table) == {("device_count", 0), ("scene_info", 1), ("scene_upload", 2), ("scene_clone", 2), ("render", 5),
+                          ("render_pixel_list", 5), ("frame_alloc", 3), ("render_into", 4), ("frame_binary", 1)}
+    # everything that can block runs on a dirty scheduler: the host-side build is CPU-bound (1), waiting for the
+    # GPU is IO-bound (2)
+    assert table[("scene_upload", 2)] == 1
+    for name in (("scene_clone", 2), ("render", 5), ("render_pixel_list", 5), ("render_into", 4), ("frame_alloc", 3)):
+        assert table[name] == 2, name
+
+
+def test_hot_code_upgrade_takes_the_resource_types_over(beam):
+    # load() ran once in the fixture: the types exist.  A second plain load must fail (ERL_NIF_RT_CREATE on an
+    # existing type), upgrade() must succeed (CREATE | TAKEOVER).
+    import ctypes
+    assert beam.entry.load(beam.env, None, 0) != 0
+    up = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)(beam.entry.upgrade)
+    assert up(beam.env, None, None, 0) == 0
+
+
+def test_a_million_element_scene_is_decoded_with_exact_tables(beam):
+    # decode_scene sizes its tables by a counting pass; a list of junk must not allocate per-kind tables of its length
+    n = 200000
+    scene = [sc.demo_scene()[0]] + [('fog', k) for k in range(n)] + sc.demo_scene()[1:]
+    assert beam.call("scene_info", scene) == (2, 3, 1, 1)
 
 
 def test_scene_decode_accepts_the_reference_records(beam):
@@ -102,6 +121,20 @@ def test_render_through_the_nif_matches_the_c_abi(beam, gpu):
                  ("not_a_handle", 4, 4, 1, [])):
         with pytest.raises(Badarg):
             beam.call("render", *args)
+    # one shared page-locked frame filled part by part through a clone of the scene (what render_binary/5 does)
+    ok, clone = beam.call("scene_clone", handle, 0)
+    assert ok == "ok" and isinstance(clone, Resource)
+    ok, frame = beam.call("frame_alloc", w, h, "rgb8")
+    assert ok == "ok" and isinstance(frame, Resource)
+    for part, hdl in ((0, handle), (1, clone), (2, handle)):
+        assert beam.call("render_into", hdl, frame, 1, [("part", (4, 3, part)), ("camera", cam)]) == "ok"
+    assert beam.call("frame_binary", frame) == want_cam.tobytes()
+    with pytest.raises(Badarg):
+        beam.call("render_into", handle, frame, 1, [("format", "f64")])        # the frame is rgb8
+    with pytest.raises(Badarg):
+        beam.call("scene_clone", "not_a_handle", 0)
+    beam.gc(clone)
+    beam.gc(frame)
     beam.gc(handle)          # the resource destructor frees the device scene
     with pytest.raises(Badarg):
         beam.call("render", handle, 4, 4, 1, [])

@@ -36,5 +36,42 @@ def main():
     dev.close()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "split"):
     main()
+
+
+def split_probe():
+    """Two sub-parts of one part on two slots (streams) at once, against the part on one slot: host wall time."""
+    import time
+    wl = sys.argv[2] if len(sys.argv) > 2 else "c4"
+    n_parts = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    reps = 12
+    w, h, depth = 3840, 2160, 5
+    flat = sc.synthetic_scene(wl)
+    dev = flat.upload(0)
+    band = multigpu.default_band_rows(h, n_parts)
+
+    def one():
+        dev.render_async(w, h, depth, slot=0, fmt="rgb8", accel="auto", band_rows=band, n_parts=n_parts, part=0)
+        dev.wait(0)
+
+    def two():
+        dev.render_async(w, h, depth, slot=0, fmt="rgb8", accel="auto", band_rows=band, n_parts=2 * n_parts, part=0)
+        dev.render_async(w, h, depth, slot=1, fmt="rgb8", accel="auto", band_rows=band, n_parts=2 * n_parts, part=n_parts)
+        dev.wait(0)
+        dev.wait(1)
+
+    for name, fn in (("one slot", one), ("two slots", two), ("one slot", one), ("two slots", two)):
+        ts = []
+        for i in range(reps + 3):
+            _lib.l2_flush(0)
+            t0 = time.perf_counter()
+            fn()
+            if i >= 3:
+                ts.append(1e3 * (time.perf_counter() - t0))
+        print("%s part 0 of %d, %s: wall ms median %.3f min %.3f" % (wl, n_parts, name, float(np.median(ts)), min(ts)))
+    dev.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "split":
+    split_probe()
