@@ -122,11 +122,16 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
         if (count[c] > (uint32_t)kCellGridMaxCount) { out = CellGrid(); return; }
         out.cells[c] = (run << 7) | count[c];
         cursor[c] = run;
-        run += count[c];
+        // every cell's list is stored in whole groups of kCellGridPad entries: the filter loop of the walk reads
+        // a group at a time without looking at the count (the padding is a sphere that never passes)
+        run += (count[c] + (uint32_t)kCellGridPad - 1) / (uint32_t)kCellGridPad * (uint32_t)kCellGridPad;
+        if (run >= kCellGridMaxRefs) { out = CellGrid(); return; }
     }
     // pass 3: fill, spheres in list order inside a cell
-    out.ref_filter.resize((size_t)run * 4);
-    out.ref_sph.resize((size_t)run);
+    run += (uint32_t)kCellGridPad;                   // the loop may fetch one group past the last list
+    out.ref_filter.assign((size_t)run * 4, 0.f);
+    for (size_t k = 0; k < (size_t)run; k++) out.ref_filter[k * 4 + 3] = -3.0e38f;
+    out.ref_sph.assign((size_t)run, -1);
     for (int64_t k = 0; k < n; k++) {
         if (is_big[(size_t)k]) continue;
         int i0[3], i1[3];

@@ -20,6 +20,7 @@ constexpr double kCellGridDensity = 0.35;    // default: cells per sphere (ERT_C
 constexpr int kCellGridMinSpheres = 256;     // smaller scenes do not get one
 constexpr int kCellGridMaxRes = 1024;        // cells per axis (the walk keeps plane indices as floats)
 constexpr int kCellGridMaxCount = 127;       // spheres per cell (7 bits of the packed cell word)
+constexpr int kCellGridPad = 4;              // a cell's list is stored in whole groups of this many entries
 constexpr uint32_t kCellGridMaxRefs = 1u << 25;
 constexpr int kCellGridBigCells = 512;       // a sphere overlapping more cells than this goes to the `big` list
 constexpr int kCellGridMaxBig = 32;          // more of those than this: no grid for the scene
@@ -31,8 +32,8 @@ struct CellGrid {
     float cs = 0, inv_cs = 0;                     // edge of a cell
     float eps = 0;                                // inflation of the sphere boxes; rays need 4m <= eps
     std::vector<uint32_t> cells;                  // [rx*ry*rz] (first_ref << 7) | count
-    std::vector<float> ref_filter;                // [n_refs][4] filter spheres in cell order
-    std::vector<int32_t> ref_sph;                 // [n_refs] sphere index
+    std::vector<float> ref_filter;                // [n_refs][4] filter spheres in cell order (padding: R = -3e38)
+    std::vector<int32_t> ref_sph;                 // [n_refs] sphere index (padding: -1)
     std::vector<int32_t> big;                     // spheres tested by every ray
 };
 

@@ -461,7 +461,7 @@ int upload_scene(ert_scene *s)
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true, true>, kWfThreads, 0));
         s->wf_grid[4] = prop.multiProcessorCount * std::max(nb, 1);
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path_refill<false, true>, kWfThreads, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path_refill<false, true, true>, kWfThreads, 0));
         s->wf_grid[5] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false, true>, kWfThreads, 0));
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
@@ -482,11 +482,11 @@ int upload_scene(ert_scene *s)
         if ((rc = carve((const void *)wf_trace_path<true, false, true, false>, s->wf_grid[0] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_path<false, false, true, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_path<false, false, false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        if ((rc = carve((const void *)wf_trace_path_refill<false, false>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path_refill<false, false, true>, s->wf_grid[1] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_path<true, false, true, true>, s->wf_grid[4] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_path<false, false, true, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_path<false, false, false, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
-        if ((rc = carve((const void *)wf_trace_path_refill<false, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
+        if ((rc = carve((const void *)wf_trace_path_refill<false, true, true>, s->wf_grid[5] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, true>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         if ((rc = carve((const void *)wf_trace_shadow<false, false>, s->wf_grid[2] / prop.multiProcessorCount)) != ERT_OK) return rc;
         CU(cudaFuncSetAttribute(wf_scan<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmem));
@@ -746,7 +746,12 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             CU(cudaStreamSynchronize(st));
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
+        static const bool refill_no_emit = getenv("ERT_REFILL_NO_EMIT") != nullptr;      // A/B: hit emission as its own launch
         const bool sort = b >= 1 && !no_sort && !scan;
+        const bool grid_b = cells && b >= cells_from;
+        const bool refill = b >= (grid_b ? cells_refill_from : ERT_WF_REFILL_FROM);
+        // the path kernels emit their hit records themselves unless the hits are to be binned first
+        const bool emitted = !scan && (b == 0 || (!sort && !(refill && refill_no_emit)));
         if (scan) {
             // planes/triangles seed every ray's result (counted with the other kernels), then every ray meets every sphere
             if (b == 0) wf_scan_init<false, true, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fp, wf, b);
@@ -759,17 +764,16 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         else if (cells && b >= cells_from) {
             // path rays step through the cell grid (ERT_ACCEL_GRID)
             if (b == 0) wf_trace_path<true, COUNT, true, true><<<s->wf_grid[4], kWfThreads, 0, st>>>(d, fp, wf, b);
-            else if (b < cells_refill_from && sort) wf_trace_path<false, COUNT, false, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
-            else if (b < cells_refill_from) wf_trace_path<false, COUNT, true, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
-            else wf_trace_path_refill<COUNT, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else if (!refill && !emitted) wf_trace_path<false, COUNT, false, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else if (!refill) wf_trace_path<false, COUNT, true, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else if (!emitted) wf_trace_path_refill<COUNT, true, false><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
+            else wf_trace_path_refill<COUNT, true, true><<<s->wf_grid[5], kWfThreads, 0, st>>>(d, fp, wf, b);
         }
         else if (b == 0) wf_trace_path<true, COUNT, true, false><<<s->wf_grid[0], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else if (b < ERT_WF_REFILL_FROM && sort) wf_trace_path<false, COUNT, false, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else if (b < ERT_WF_REFILL_FROM) wf_trace_path<false, COUNT, true, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        else wf_trace_path_refill<COUNT, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
-        // the batch kernels emit their hit records themselves unless the hits are to be binned
-        const bool grid_b = cells && b >= cells_from;
-        const bool emitted = !scan && (b == 0 || (b < (grid_b ? cells_refill_from : ERT_WF_REFILL_FROM) && !sort));
+        else if (!refill && !emitted) wf_trace_path<false, COUNT, false, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (!refill) wf_trace_path<false, COUNT, true, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else if (!emitted) wf_trace_path_refill<COUNT, false, false><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
+        else wf_trace_path_refill<COUNT, false, true><<<s->wf_grid[1], kWfThreads, 0, st>>>(d, fp, wf, b);
         n++;
         TICK(0);
         WF_CHECK("wf_trace_path");

@@ -235,6 +235,45 @@ __device__ __forceinline__ void scan_others(const DevScene &sc, d3 O, d3 D, Hit 
     }
 }
 
+// Planes and triangles of a shadow query (erl:256-267): `best` holds the target and the only question is whether
+// something beats its (Distance, list position).  A plane certainly farther than the target is dismissed before the
+// division of erl:468: with Vd < 0, Distance = V0 / Vd >= X  <=>  V0 <= X * Vd, and X = Distance(target) * (1 + 1e-9)
+// leaves seven decimal orders for the roundings of the products.  Everything nearer goes through the literal test.
+template <bool COUNT>
+__device__ __forceinline__ void scan_others_shadow(const DevScene &sc, d3 O, d3 D, Hit &best, int skip_obj,
+                                                   Tally<COUNT> &tl)
+{
+    for (int i = 0; i < sc.n_tris; i++) {
+        int code = obj_code(OBJ_TRIANGLE, i);
+        if (code == skip_obj) continue;
+        double t;
+        TALLY(exact_other);
+        if (triangle_exact(O, D, sc.tris + 9 * i, t)) {
+            int ord = sc.tri_order[i];
+            if (better(t, ord, best)) { best.t = t; best.order = ord; best.obj = code; }
+        }
+    }
+    for (int i = 0; i < sc.n_planes; i++) {
+        int code = obj_code(OBJ_PLANE, i);
+        if (code == skip_obj) continue;
+        TALLY(exact_other);
+        const double *p = sc.planes + 4 * i;
+        const d3 n = mk(p[0], p[1], p[2]);
+        const double vd = vdot(n, D);
+        if (!(vd < 0.0)) continue;                                   // erl:464
+        if (best.obj >= 0) {
+            if (best.t <= 0.0) continue;                             // a plane hit has Distance >= 0.001 (erl:469)
+            const double v0 = -(vdot(n, O) + p[3]);
+            if (v0 <= (best.t * (1.0 + 1e-9)) * vd) continue;        // certainly beyond the target
+        }
+        double t;
+        if (plane_exact(O, D, p, t)) {
+            int ord = sc.plane_order[i];
+            if (better(t, ord, best)) { best.t = t; best.order = ord; best.obj = code; }
+        }
+    }
+}
+
 // the literal test of one known object (used to seed shadow queries with their target)
 __device__ __forceinline__ bool object_exact(const DevScene &sc, int code, d3 O, d3 D, double a, double &t)
 {

@@ -140,7 +140,7 @@ wf_scan_init(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
             bool occluded = true;
             if (object_exact(sc, target, O, D, a, t)) {
                 best.t = t; best.order = target_order; best.obj = target;
-                scan_others<COUNT>(sc, O, D, best, target, tl);
+                scan_others_shadow<COUNT>(sc, O, D, best, target, tl);
                 occluded = best.obj != target;
             }
             wf.sp_occ[i] = occluded ? 1 : 0;

@@ -34,6 +34,11 @@
 #endif
 
 namespace ert {
+#ifdef ERT_FILTER_OLD
+#define GRID_EXACT_FN grid_exact_old
+#else
+#define GRID_EXACT_FN grid_exact
+#endif
 
 // One hit of a path ray, in two records: the shadow stage streams only the 32-byte heads
 // (dense, every fetched byte used), the shade stage reads both.
@@ -430,8 +435,9 @@ __device__ __forceinline__ float grid_advance(GridWalk &g, const GridRay &r, con
 // instead of one at a time.  A sphere is listed in every cell it overlaps, so the incumbent itself
 // comes by again: it is skipped.  Once the incumbent has improved inside the cell the remaining
 // survivors go through the filter's distance cull again before their FP64 test.
+#ifdef ERT_FILTER_OLD
 template <bool COUNT>
-__device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SRay &f, int first, int cnt, float cullk,
+__device__ __forceinline__ unsigned int grid_filter_old(const DevScene &sc, const SRay &f, int first, int cnt, float cullk,
                                                     Tally<COUNT> &tl)
 {
     const float4 *fp4 = sc.cg.ref_filter + first;
@@ -455,7 +461,7 @@ __device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SR
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
+__device__ __forceinline__ void grid_exact_old(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
                                            unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
@@ -480,6 +486,66 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
                 best.t = t; best.order = ord; best.obj = code;
                 cullk = cullk_from(f, ray.inv_sqrt_a(), best);
                 improved = true;
+            }
+        }
+    }
+}
+
+#endif
+template <bool COUNT>
+__device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SRay &f, int first, int cnt, Tally<COUNT> &tl)
+{
+    // Stage 1 only, four spheres per round and no branch inside: the lists are stored in whole groups of four
+    // (kCellGridPad; the padding never passes), the pass bits go into the survivor mask with selects.  Stage 2
+    // (behind the origin / beyond the incumbent) waits for grid_exact, where it sees the newest cull distance.
+    static_assert(kCellGridPad == 4, "the filter loop reads groups of four");
+    const float4 *fp4 = sc.cg.ref_filter + first;
+    const float nth = -f.theta;
+    unsigned int surv = 0u;
+    float4 s0 = __ldg(fp4), s1 = __ldg(fp4 + 1), s2 = __ldg(fp4 + 2), s3 = __ldg(fp4 + 3);
+#pragma unroll 1
+    for (int k = 0; k < cnt; k += 4) {
+        // the next group is in flight while this one is tested (one group past the list at the end: it exists)
+        const float4 n0 = __ldg(fp4 + k + 4), n1 = __ldg(fp4 + k + 5), n2 = __ldg(fp4 + k + 6), n3 = __ldg(fp4 + k + 7);
+        float b, v0, v1, v2, v3;
+        filter_stage1(f, s0, b, v0);
+        filter_stage1(f, s1, b, v1);
+        filter_stage1(f, s2, b, v2);
+        filter_stage1(f, s3, b, v3);
+        const unsigned int m = (v0 < nth ? 0u : 1u) | (v1 < nth ? 0u : 2u) | (v2 < nth ? 0u : 4u) | (v3 < nth ? 0u : 8u);
+        surv |= m << k;
+        s0 = n0; s1 = n1; s2 = n2; s3 = n3;
+    }
+    if constexpr (COUNT) tl.filter += cnt;
+    return surv;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
+                                           unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
+{
+    const DevScene::CellGridDev &cg = sc.cg;
+    while (surv) {
+        const int k = __ffs((int)surv) - 1;
+        surv &= surv - 1u;
+        const int slot = first + k;
+        const int sph = __ldg(cg.ref_sph + slot);
+        if (sph < 0) continue;                           // padding (only a NaN ray gets here)
+        const int code = obj_code(OBJ_SPHERE, sph);
+        if (code == skip_obj || code == best.obj) continue;
+        {
+            const float4 fs = __ldg(cg.ref_filter + slot);
+            float b, v;
+            filter_stage1(f, fs, b, v);
+            if (!filter_stage2(f, fs, b, v, cullk)) continue;
+        }
+        double t;
+        TALLY(exact_sph);
+        if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+            const int ord = sc.sph_order[sph];
+            if (better(t, ord, best)) {
+                best.t = t; best.order = ord; best.obj = code;
+                cullk = cullk_from(f, ray.inv_sqrt_a(), best);
             }
         }
     }
@@ -513,11 +579,20 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
     int cnt = (int)(c & 127u);
     while (cnt > 32) {
         // rare: more than one mask's worth of spheres in the cell; all but the last 32 are finished here
-        const unsigned int sv = grid_filter<COUNT>(sc, f, first, 32, g.cullk, tl);
+#ifdef ERT_FILTER_OLD
+        const unsigned int sv = grid_filter_old<COUNT>(sc, f, first, 32, g.cullk, tl);
+        grid_exact_old<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
+#else
+        const unsigned int sv = grid_filter<COUNT>(sc, f, first, 32, tl);
         grid_exact<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
+#endif
         first += 32; cnt -= 32;
     }
-    surv = grid_filter<COUNT>(sc, f, first, cnt, g.cullk, tl);
+#ifdef ERT_FILTER_OLD
+    surv = grid_filter_old<COUNT>(sc, f, first, cnt, g.cullk, tl);
+#else
+    surv = grid_filter<COUNT>(sc, f, first, cnt, tl);
+#endif
     return true;
 }
 __device__ __forceinline__ bool grid_leave(GridWalk &g, float te)
@@ -535,7 +610,7 @@ __device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const D
     int first;
     float te;
     if (!grid_find<COUNT>(g, r, sc, ray, f, best, skip_obj, tl, surv, first, te)) return true;
-    grid_exact<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
+    GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
     return grid_leave(g, te);
 }
 
@@ -771,17 +846,21 @@ __global__ void __launch_bounds__(kWfThreads) wf_bin_scatter(const __grid_consta
 }
 
 // ------------------------------------------------------------------ shadow queries by direction
-// Cell of a direction in a light's cube map; restates light_grid_cell() of light_grid.cpp.
-__device__ __forceinline__ unsigned int light_grid_cell_dev(d3 D, int res)
+// Cell of a direction in a light's cube map, in FP32 from the filter ray's direction: the operations of
+// light_grid_cell_f32() in light_grid.cpp (whose slack covers their rounding; tests/test_light_grid.py checks the
+// listing with this very computation).  Two FP64 divisions per shadow ray became one FP32 reciprocal.
+__device__ __forceinline__ unsigned int light_grid_cell_dev(const SRay &f, int res)
 {
-    double ax = fabs(D.x), ay = fabs(D.y), az = fabs(D.z);
+    const float ax = fabsf(f.dx), ay = fabsf(f.dy), az = fabsf(f.dz);
     int m = 0;
-    double am = ax, dm = D.x, du = D.y, dv = D.z;
-    if (ay > am) { m = 1; am = ay; dm = D.y; du = D.z; dv = D.x; }
-    if (az > am) { m = 2; am = az; dm = D.z; du = D.x; dv = D.y; }
-    int face = 2 * m + (dm < 0.0 ? 1 : 0);
-    double u = du / am, v = dv / am;
-    int iu = (int)floor((u + 1.0) * 0.5 * (double)res), iv = (int)floor((v + 1.0) * 0.5 * (double)res);
+    float am = ax, dm = f.dx, du = f.dy, dv = f.dz;
+    if (ay > am) { m = 1; am = ay; dm = f.dy; du = f.dz; dv = f.dx; }
+    if (az > am) { m = 2; am = az; dm = f.dz; du = f.dx; dv = f.dy; }
+    const int face = 2 * m + (dm < 0.0f ? 1 : 0);
+    const float inv = __frcp_rn(am);
+    const float u = du * inv, v = dv * inv;
+    const float half = 0.5f * (float)res;
+    int iu = (int)floorf((u + 1.0f) * half), iv = (int)floorf((v + 1.0f) * half);
     iu = min(max(iu, 0), res - 1);
     iv = min(max(iv, 0), res - 1);
     return (unsigned int)((face * res + iv) * res + iu);
@@ -796,7 +875,7 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
                                                     Tally<COUNT> &tl)
 {
     const float cull0 = cullk_from(f, inv_sqrt_a, best);
-    const unsigned int cell = light_grid_cell_dev(D, lg.res);
+    const unsigned int cell = light_grid_cell_dev(f, lg.res);
     // the head of the cell carries its nearest candidate and the range of the others: one dependent
     // fetch for the rays that the first candidate settles (most of them)
     float c[8];
@@ -968,7 +1047,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     bool found = false;
                     if (walking) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, skip, tl, surv, first, te);
                     __syncwarp();
-                    if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
+                    if (surv) GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
                     if (walking) walking = found ? !grid_leave(gw, te) : false;
                 }
             }
@@ -1011,12 +1090,24 @@ constexpr int kRefillBelow = ERT_WF_REFILL;
 #ifndef ERT_WF_REFILL_MINBLOCKS
 #define ERT_WF_REFILL_MINBLOCKS 4
 #endif
-template <bool COUNT, bool GRID>
+// EMIT: rays whose walk is over do not leave their result in HBM for wf_emit_hits; the hits wait in a small
+// per-warp queue and, 32 at a time, one per lane, become hit records (location and normal in FP64 on a full warp,
+// one atomic per 32 hits, coalesced record stores).
+struct alignas(16) FinishedHit {
+    double t;
+    unsigned int idx;           // entry of the path queue
+    int obj;
+};
+constexpr int kFinQueue = 64;   // up to 31 waiting + 32 lanes finishing in one step
+template <bool COUNT, bool GRID, bool EMIT>
 __global__ void __launch_bounds__(kWfThreads, GRID ? ERT_GRID_MINBLOCKS : ERT_WF_REFILL_MINBLOCKS)
 wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                      const __grid_constant__ WfBuf wf, int bounce)
 {
     __shared__ double slots[kRaySlotDoubles][kWfThreads];
+    __shared__ FinishedHit fin_all[EMIT ? kWfThreads / 32 : 1][EMIT ? kFinQueue : 1];
+    FinishedHit *fin = fin_all[EMIT ? (threadIdx.x >> 5) : 0];
+    int n_fin = 0;                                   // the same in every lane
     RaySlot ray;
     ray.p = &slots[0][threadIdx.x];
     unsigned int *ctr = wf.ctr + bounce * kWfCtr;
@@ -1038,6 +1129,31 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
     GridWalk gw;
     GridRay gr;
     gw.id = -1;
+    // turns the first `take` queued hits into hit records, one per lane (erl:384-390, 443-451, 471-476)
+    auto emit_finished = [&](int take) {
+        __syncwarp();
+        unsigned int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)take);
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (lane < take) {
+            const FinishedHit fh = fin[lane];
+            d3 O, D;
+            int pid;
+            bool valid;
+            path_ray_of_index(fp, wf, false, fh.idx, O, D, pid, valid);
+            const d3 P = vadd(O, vscale(D, fh.t));
+            const d3 N = hit_normal(sc, fh.obj, P);
+            write_hit(wf.hit_head, wf.hit_tail, slot0 + lane, P, N, D, fh.obj, object_order(sc, fh.obj), pid);
+        }
+        __syncwarp();
+        FinishedHit keep;
+        keep.t = 0.0; keep.idx = 0u; keep.obj = -1;
+        if (take + lane < n_fin) keep = fin[take + lane];
+        __syncwarp();
+        if (take + lane < n_fin) fin[lane] = keep;
+        n_fin -= take;
+        __syncwarp();
+    };
     for (;;) {
         const unsigned int idle = __ballot_sync(0xffffffffu, !have);
         if (32 - __popc(idle) < kRefillBelow && !drained) {
@@ -1076,11 +1192,12 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                         } else {
                             trav_start(tr, stack, f, inv, best);
                         }
-                        have = true;
                     } else {
-                        wf.res_hit[i] = make_int2(best.obj, best.order);
-                        wf.res_t[i] = best.t;
+                        // no spheres: the first step below reports the ray as done (planes and triangles are in `best`)
+                        gw.id = -1;
+                        tr.node = kTravDone;
                     }
+                    have = true;
                 }
             }
         }
@@ -1099,12 +1216,25 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                 bool found = false;
                 if (have) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, -1, tl, surv, first, te);
                 __syncwarp();
-                if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
+                if (surv) GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
                 if (have) over = found ? grid_leave(gw, te) : true;
             } else {
                 if (have) over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
             }
-            if (over) {
+            if constexpr (EMIT) {
+                const bool fin_hit = over && best.obj >= 0;
+                const unsigned int fm = __ballot_sync(0xffffffffu, fin_hit);
+                if (fm) {
+                    if (fin_hit) {
+                        FinishedHit fh;
+                        fh.t = best.t; fh.idx = idx; fh.obj = best.obj;
+                        fin[n_fin + rank_in(fm, lane)] = fh;
+                    }
+                    n_fin += __popc(fm);
+                    if (n_fin >= 32) emit_finished(32);
+                }
+                if (over) have = false;
+            } else if (over) {
                 __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
                 __stcs(wf.res_t + idx, best.t);
                 have = false;
@@ -1112,6 +1242,9 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
             const int act = __popc(__ballot_sync(0xffffffffu, have));
             if (act == 0 || (!drained && act < kRefillBelow)) break;
         }
+    }
+    if constexpr (EMIT) {
+        if (n_fin > 0) emit_finished(n_fin);
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
@@ -1242,7 +1375,7 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 if (object_exact(sc, target, O, D, a, t)) {
                     Hit best;
                     best.t = t; best.order = order; best.obj = target;
-                    scan_others<COUNT>(sc, O, D, best, target, tl);
+                    scan_others_shadow<COUNT>(sc, O, D, best, target, tl);
                     lit = best.obj == target;
                     if (lit && hint >= 0 && obj_code(OBJ_SPHERE, hint) != target) {
                         double th;

@@ -12,8 +12,13 @@ namespace ert {
 namespace {
 
 constexpr double kQuarterPi = 0.78539816339744830962;
-constexpr double kAngleSlack = 1e-7;      // radians added to every half-angle
-constexpr double kCoordSlack = 1e-9;      // added to the projected bounds
+// Shadow rays find their cell in FP32 (light_grid_cell_f32: direction rounded to float, one reciprocal, two
+// products — every step within 6e-8 relative, |u| <= 1, so the cell coordinate is off by < 5e-7, and a direction
+// that close to a face edge may land on the neighbouring face).  The slack below is four times that, on the
+// half-angle and on the projected bounds, so a sphere is listed in every cell the FP32 computation can name for a
+// direction that touches it.
+constexpr double kAngleSlack = 2e-6;      // radians added to every half-angle
+constexpr double kCoordSlack = 2e-6;      // added to the projected bounds
 
 struct Rect { int32_t sphere; uint8_t face; uint16_t u0, u1, v0, v1; };
 
@@ -51,6 +56,24 @@ int64_t light_grid_cell(const double d[3], int res)
     int face = 2 * m + (d[m] < 0.0 ? 1 : 0);
     double u = d[(m + 1) % 3] / am, v = d[(m + 2) % 3] / am;
     return ((int64_t)face * res + cell_index(v, res)) * res + cell_index(u, res);
+}
+
+// The cell a shadow ray looks in, as the device computes it (same IEEE operations: wf_trace_shadow).
+int64_t light_grid_cell_f32(const float d[3], int res)
+{
+    const float ax = std::fabs(d[0]), ay = std::fabs(d[1]), az = std::fabs(d[2]);
+    int m = 0;
+    float am = ax;
+    if (ay > am) { m = 1; am = ay; }
+    if (az > am) { m = 2; am = az; }
+    const int face = 2 * m + (d[m] < 0.0f ? 1 : 0);
+    const float inv = 1.0f / am;
+    const float u = d[(m + 1) % 3] * inv, v = d[(m + 2) % 3] * inv;
+    const float half = 0.5f * (float)res;
+    int iu = (int)std::floor((u + 1.0f) * half), iv = (int)std::floor((v + 1.0f) * half);
+    iu = std::min(std::max(iu, 0), res - 1);
+    iv = std::min(std::max(iv, 0), res - 1);
+    return ((int64_t)face * res + iv) * res + iu;
 }
 
 bool build_light_grid(const double *centers, const double *radii, const float *filter, int64_t n,

@@ -40,5 +40,7 @@ bool build_light_grid(const double *centers, const double *radii, const float *f
 // major axis m = first axis of largest |d|, face = 2*m + (d[m] < 0), u = d[(m+1)%3]/|d[m]|,
 // v = d[(m+2)%3]/|d[m]|, cell = (face*res + iv)*res + iu with i = floor((x+1)*res/2) clamped.
 int64_t light_grid_cell(const double d[3], int res);
+// The same in FP32, operation for operation what the shadow kernel does with the filter ray's direction.
+int64_t light_grid_cell_f32(const float d[3], int res);
 
 }  // namespace ert

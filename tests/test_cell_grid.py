@@ -155,8 +155,15 @@ def test_every_sphere_is_listed_in_every_cell_it_reaches(cg):
     assert g.enabled and len(g.big) == 0
     counts = g.cells & 127
     firsts = g.cells >> 7
-    assert np.array_equal(firsts, np.concatenate([[0], np.cumsum(counts)[:-1]]))
-    assert counts.sum() == len(g.ref_sph)
+    # every list is stored in whole groups of four entries (the walk's filter loop reads a group at a time); the
+    # padding has no sphere, and one more group follows the last list
+    padded = (counts + 3) // 4 * 4
+    assert np.array_equal(firsts, np.concatenate([[0], np.cumsum(padded)[:-1]]))
+    assert padded.sum() + 4 == len(g.ref_sph)
+    assert counts.sum() == int((g.ref_sph >= 0).sum())
+    for c_id in rng.integers(0, len(counts), 200).tolist():
+        lst = g.ref_sph[firsts[c_id]:firsts[c_id] + padded[c_id]]
+        assert np.all(lst[:counts[c_id]] >= 0) and np.all(lst[counts[c_id]:] == -1)
     # bounds contain every sphere box; cells cover the bounds
     assert np.all(g.lo < (c - r[:, None]).min(axis=0)) and np.all(g.hi > (c + r[:, None]).max(axis=0))
     assert np.all(g.res * np.float64(g.cs) >= g.hi.astype(np.float64) - g.lo.astype(np.float64))

@@ -32,6 +32,8 @@ def lg():
     L.lg_free.argtypes = [vp]
     L.lg_cell.restype = ctypes.c_longlong
     L.lg_cell.argtypes = [vp, ctypes.c_int]
+    L.lg_cell_f32.restype = ctypes.c_longlong
+    L.lg_cell_f32.argtypes = [vp, ctypes.c_int]
     for name in ("lg_n_entries", "lg_n_always"):
         getattr(L, name).restype = ctypes.c_longlong
         getattr(L, name).argtypes = [vp]
@@ -66,6 +68,12 @@ def cells_of(L, dirs, res):
     return np.array([L.lg_cell(dirs[i].ctypes.data, res) for i in range(len(dirs))], dtype=np.int64)
 
 
+def cells_of_f32(L, dirs, res, scale=1.0000019073486328):
+    """The cell the shadow kernel computes: the direction scaled like the filter ray (K_D), rounded to float32."""
+    d32 = np.ascontiguousarray(np.asarray(dirs, dtype=np.float64) * scale, dtype=np.float32)
+    return np.array([L.lg_cell_f32(d32[i].ctypes.data, res) for i in range(len(d32))], dtype=np.int64)
+
+
 def touched(light, d, centers, radii):
     """Spheres the ray light + s*d (s >= 0, |d| = 1) touches, geometrically, in double."""
     oc = centers - light
@@ -98,13 +106,18 @@ def test_every_touched_sphere_is_listed(lg, res):
     dirs = np.concatenate([d, rim, special])
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
     cells = cells_of(lg, dirs, res)
+    cells32 = cells_of_f32(lg, dirs, res)
     assert cells.min() >= 0 and cells.max() < 6 * res * res
+    assert cells32.min() >= 0 and cells32.max() < 6 * res * res
+    assert (cells32 != cells).mean() < 0.01            # they differ only for directions on a cell boundary
     n_touch = 0
     for k in range(len(dirs)):
-        listed = set(ent["sphere"][off[cells[k]]:off[cells[k] + 1]].tolist()) | set(always.tolist())
         hit = touched(light, dirs[k], centers, radii)
         n_touch += len(hit)
-        assert set(hit.tolist()) <= listed, (k, dirs[k])
+        # the FP64 cell (host builder's own rule) and the FP32 cell the shadow kernel looks in
+        for c in (cells[k], cells32[k]):
+            listed = set(ent["sphere"][off[c]:off[c + 1]].tolist()) | set(always.tolist())
+            assert set(hit.tolist()) <= listed, (k, dirs[k])
     assert n_touch > 3000
 
 
