@@ -65,6 +65,7 @@ struct HostScene {
     std::vector<int> tri_order;
     std::vector<double> sph_exact;     // [n][4]
     std::vector<double> sph_mat;       // [n][6]
+    std::vector<double> sph_refl;      // [n]
     std::vector<int> sph_order;
     std::vector<float> sph_filter;     // [n][4]
     std::vector<float> sph_pairs;      // pair-interleaved, padded to whole scan tiles (ert_scan.cuh)
@@ -79,6 +80,8 @@ struct HostScene {
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                // shadow + shading of bounce b, while `stream` traces bounce b+1
+    std::vector<cudaEvent_t> ev_path, ev_shade;    // per bounce: hits of the bounce emitted / colours of the bounce folded
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     void *fb = nullptr;
     size_t fb_cap = 0;
@@ -231,6 +234,7 @@ int flatten(const ert_scene_desc *d, HostScene &h)
     h.n_spheres = (int)d->n_spheres;
     h.sph_exact.resize((size_t)h.n_spheres * 4);
     h.sph_mat.resize((size_t)h.n_spheres * 6);
+    h.sph_refl.resize((size_t)h.n_spheres);
     h.sph_order.resize((size_t)h.n_spheres);
     h.sph_filter.resize((size_t)h.n_spheres * 4);
     std::vector<double> centers((size_t)h.n_spheres * 3), radii((size_t)h.n_spheres);
@@ -243,6 +247,7 @@ int flatten(const ert_scene_desc *d, HostScene &h)
         double *m = &h.sph_mat[(size_t)k * 6];
         m[0] = s.material.colour[0]; m[1] = s.material.colour[1]; m[2] = s.material.colour[2];
         m[3] = s.material.specular_power; m[4] = s.material.shininess; m[5] = s.material.reflectivity;
+        h.sph_refl[(size_t)k] = s.material.reflectivity;
         h.sph_order[(size_t)k] = s.order;
         float pad_c, eta_c;
         make_filter_sphere(s.center, s.radius, &h.sph_filter[(size_t)k * 4], pad_c, eta_c);
@@ -377,6 +382,7 @@ int upload_scene(ert_scene *s)
     UP(h.tri_order, tri_order, int);
     UP(h.sph_exact, sph_exact, double);
     UP(h.sph_mat, sph_mat, double);
+    UP(h.sph_refl, sph_refl, double);
     UP(h.sph_order, sph_order, int);
     UP(h.sph_filter, sph_filter, float);
     UP(h.sph_pairs, sph_pairs, float);
@@ -439,7 +445,14 @@ int upload_scene(ert_scene *s)
     d.r_max = h.r_max; d.pad_c_max = h.pad_c_max; d.eta_c_max = h.eta_c_max; d.abs_max = h.abs_max;
     for (int i = 0; i < ERT_MAX_SLOTS; i++) {
         Slot &sl = s->slots[i];
-        CU(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        {
+            // the path rays are the critical chain of a frame: their stream gets the higher priority, the shadow rays
+            // and the shading of the previous bounce fill what the path kernels leave idle
+            int prio_lo = 0, prio_hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CU(cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, prio_hi));
+            CU(cudaStreamCreateWithPriority(&sl.stream2, cudaStreamNonBlocking, prio_lo));
+        }
         CU(cudaEventCreate(&sl.ev0));
         CU(cudaEventCreate(&sl.ev1));
         CU(cudaEventCreate(&sl.ev2));
@@ -523,6 +536,9 @@ void destroy(ert_scene *s)
         if (sl.wf_ctr_host) cudaFreeHost(sl.wf_ctr_host);
         if (sl.wf_ctr_all_host) cudaFreeHost(sl.wf_ctr_all_host);
         for (cudaEvent_t e : sl.ticks) cudaEventDestroy(e);
+        for (cudaEvent_t e : sl.ev_path) cudaEventDestroy(e);
+        for (cudaEvent_t e : sl.ev_shade) cudaEventDestroy(e);
+        if (sl.stream2) cudaStreamDestroy(sl.stream2);
         if (sl.counters_dev) cudaFree(sl.counters_dev);
         if (sl.counters_host) cudaFreeHost(sl.counters_host);
         if (sl.ev0) cudaEventDestroy(sl.ev0);
@@ -625,12 +641,12 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf, bool sc
     size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
     if (n_pad >= ((size_t)1 << 31)) return fail(ERT_ERR_BADARG, "frame part has more than 2^31 pixels");
     size_t L = (size_t)std::max(s->host.n_lights, 1);
-    // layout: C[3] W[1] q_ray[6] res_t[1] doubles | hits, raw_hits records | q_pid res_hit[2] r_key ints |
+    // layout: C[3] res_t[1] q_ray[6]x2 q_w[1]x2 doubles | hits, raw_hits records | q_pid x2 res_hit[2] r_key ints |
     // lit bytes | sort histogram + block sums
     size_t off = 0;
-    size_t o_dbl = off; off += align_up(n_pad * 11 * sizeof(double), 256);
+    size_t o_dbl = off; off += align_up(n_pad * 18 * sizeof(double), 256);
     size_t o_rec = off; off += align_up(n_pad * 2 * (sizeof(HitHead) + sizeof(HitTail)), 256);
-    size_t o_int = off; off += align_up(n_pad * 4 * sizeof(int), 256);
+    size_t o_int = off; off += align_up(n_pad * 5 * sizeof(int), 256);
     size_t o_lit = off; off += align_up(n_pad * L, 256);
     size_t o_hist = off; off += align_up(((size_t)kSortCells + kSortBlocks) * sizeof(unsigned int), 256);
     if (sl.wf_cap < off) {
@@ -656,10 +672,11 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf, bool sc
     int *i = (int *)(base + o_int);
     wf.n_pad = (int)n_pad;
     wf.tiles_x = tiles_x;
-    wf.C = d; wf.W = d + 3 * n_pad; wf.q_ray = d + 4 * n_pad; wf.res_t = d + 10 * n_pad;
+    wf.C = d; wf.res_t = d + 3 * n_pad;
+    wf.q_ray = d + 4 * n_pad; wf.nq_ray = d + 10 * n_pad; wf.q_w = d + 16 * n_pad; wf.nq_w = d + 17 * n_pad;
     wf.hit_head = (HitHead *)(base + o_rec); wf.raw_head = wf.hit_head + n_pad;
     wf.hit_tail = (HitTail *)(wf.raw_head + n_pad); wf.raw_tail = wf.hit_tail + n_pad;
-    wf.q_pid = i; wf.res_hit = (int2 *)(i + n_pad); wf.r_key = (unsigned int *)(i + 3 * n_pad);
+    wf.q_pid = i; wf.nq_pid = i + n_pad; wf.res_hit = (int2 *)(i + 2 * n_pad); wf.r_key = (unsigned int *)(i + 4 * n_pad);
     wf.lit = base + o_lit;
     wf.hist = (unsigned int *)(base + o_hist);
     wf.sums = wf.hist + kSortCells;
@@ -738,7 +755,35 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             }                                                                          \
         }                                                                              \
     } while (0)
+    const WfBuf wf_even = wf;
+    WfBuf wf_odd = wf;
+    std::swap(wf_odd.q_pid, wf_odd.nq_pid); std::swap(wf_odd.q_ray, wf_odd.nq_ray); std::swap(wf_odd.q_w, wf_odd.nq_w);
+    // Two chains per frame.  The reflection rays of bounce b+1 exist as soon as the hits of bounce b do (they do not
+    // depend on the shadow rays), so `st` goes straight on to the next bounce's path rays while `st2` answers the
+    // shadow rays of bounce b and folds its colours: the tails of the path launches, where a few long walks keep
+    // most of the machine idle, fill with shadow rays.  The hit queue then alternates between its two buffer sets
+    // (a bounce's records are read until its shading is done).  Not when the hits are binned (the second set is the
+    // binning's), not for the brute-force scan (it shares its result arrays between the two kinds of ray), and not
+    // when every launch is timed on its own.
+    static const bool env_no_overlap = getenv("ERT_WF_NO_OVERLAP") != nullptr;
+    const bool overlap = !env_no_overlap && !timed && !scan && no_sort && fp.depth > 1 && d.n_lights > 0 && !debug_sync;
+    cudaStream_t st2 = overlap ? sl.stream2 : st;
+    if (overlap) {
+        std::swap(wf_odd.hit_head, wf_odd.raw_head);
+        std::swap(wf_odd.hit_tail, wf_odd.raw_tail);
+        while ((int)sl.ev_path.size() < fp.depth) {
+            cudaEvent_t e1, e2;
+            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            sl.ev_path.push_back(e1);
+            sl.ev_shade.push_back(e2);
+        }
+    }
+    int last_shaded = -1;
     for (int b = 0; b < fp.depth; b++) {
+        // bounce b reads the path queue the emitters of bounce b-1 wrote and writes the other one
+        wf = (b & 1) ? wf_odd : wf_even;
+        if (overlap && b >= 2) CU(cudaStreamWaitEvent(st, sl.ev_shade[(size_t)b - 2], 0));   // its hit buffers are free again
         if (b >= 8) {
             // deep recursions: stop launching once the path queue has run dry
             CU(cudaMemcpyAsync(sl.wf_ctr_host, wf.ctr + (size_t)(b - 1) * kWfCtr, kWfCtr * sizeof(unsigned int),
@@ -801,25 +846,33 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         n++;
         TICK(2);
         WF_CHECK("wf_emit_hits / wf_bin_*");
+        if (overlap) {
+            // the hits and the next rays of this bounce exist: the other stream takes the shadow rays from here
+            CU(cudaEventRecord(sl.ev_path[(size_t)b], st));
+            CU(cudaStreamWaitEvent(st2, sl.ev_path[(size_t)b], 0));
+        }
         if (scan) {
-            wf_scan_init<true, false, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fps, wf, b);
+            wf_scan_init<true, false, COUNT><<<s->wf_grid[3], 256, 0, st2>>>(d, fps, wf, b);
             n++;
             TICK(2);
-            wf_scan<true, false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st>>>(d, fps, wf, b);
+            wf_scan<true, false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st2>>>(d, fps, wf, b);
         }
-        else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
-        else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st>>>(d, fps, wf, b);
+        else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st2>>>(d, fps, wf, b);
+        else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st2>>>(d, fps, wf, b);
         TICK(1);
         WF_CHECK("wf_trace_shadow");
         if (scan) {
-            wf_scan_finish<true, false><<<s->wf_grid[3], 256, 0, st>>>(d, wf, b);
+            wf_scan_finish<true, false><<<s->wf_grid[3], 256, 0, st2>>>(d, wf, b);
             n++;
         }
-        wf_shade<<<s->wf_grid[3], kWfThreads, 0, st>>>(d, fp, wf, b);
+        wf_shade<<<s->wf_grid[3], kWfThreads, 0, st2>>>(d, fp, wf, b);
+        if (overlap) CU(cudaEventRecord(sl.ev_shade[(size_t)b], st2));
+        last_shaded = b;
         n += 2;
         TICK(2);
         WF_CHECK("wf_shade");
     }
+    if (overlap && last_shaded >= 0) CU(cudaStreamWaitEvent(st, sl.ev_shade[(size_t)last_shaded], 0));
     wf_finalize<<<s->wf_grid[3], kWfThreads, 0, st>>>(fp, wf);
     n++;
     TICK(2);

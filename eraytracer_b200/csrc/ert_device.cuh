@@ -42,6 +42,8 @@ struct DevScene {
     int n_spheres;
     const double4 *sph_exact;    // {cx, cy, cz, radius}
     const double *sph_mat;       // [n][6] colour rgb, specular_power, shininess, reflectivity
+    const double *sph_refl;      // [n] reflectivity again, dense: the emitters of the wavefront need nothing else of the
+                                 // material, and 8 bytes per sphere stay in L2 where 48-byte rows do not
     const int *sph_order;        // list position
     const float4 *sph_filter;    // {fl(cx), fl(cy), fl(cz), R} — see make_filter_sphere()
     const float4 *sph_pairs;     // the same list pair-interleaved for the packed scan (ert_scan.cuh): spheres 2p, 2p+1 as
@@ -534,6 +536,16 @@ __device__ __forceinline__ void pix_init(Pix &p, const DevScene &sc, const Frame
     p.alive = inside && fp.depth > 0;
     if (inside) primary_ray(fp, X, Y, p.O, p.D);
     else { p.O = mk(0, 0, 0); p.D = mk(0, 0, 1); }
+}
+
+__device__ __forceinline__ double reflectivity_of(const DevScene &sc, int code)
+{
+    int i = obj_index(code);
+    switch (obj_type(code)) {
+    case OBJ_SPHERE: return __ldg(sc.sph_refl + i);
+    case OBJ_PLANE: return sc.plane_mat[6 * (size_t)i + 5];
+    default: return sc.tri_mat[6 * (size_t)i + 5];
+    }
 }
 
 __device__ __forceinline__ const double *material_ptr(const DevScene &sc, int code)

@@ -50,7 +50,7 @@ struct alignas(32) HitTail {
     double N[3];                // normal
     int pid, pad0;              // pixel of the path
     double D[3];                // direction of the ray that hit
-    double pad1;
+    double W;                   // weight of the path up to this hit: product of (lights * reflectivity) of earlier bounces
 };
 static_assert(sizeof(HitHead) == 32 && sizeof(HitTail) == 64, "hit records are 32 + 64 bytes");
 
@@ -64,9 +64,15 @@ struct WfBuf {
     int n_pad;                  // pixels of this part padded to whole 8x4 tiles: tiles * 32
     int tiles_x;                // tiles per row of tiles
     double *C;                  // [3][n_pad] colour so far, by pixel
-    double *W;                  // [n_pad]    product of (lights * reflectivity) of earlier bounces
-    int *q_pid;                 // path queue: pixel of each ray
+    // path queue of the bounce being traced (read) and of the next one (written by whoever emits the hits): two
+    // buffer sets that swap every bounce, so that the next rays exist as soon as their hits do — the reflection
+    // (erl:219-221) does not depend on the shadow rays, only the colour does
+    int *q_pid;                 // pixel of each ray
     double *q_ray;              // [6][n_pad] origin xyz, direction xyz
+    double *q_w;                // [n_pad] weight of the path: product of (lights * reflectivity) of earlier bounces
+    int *nq_pid;
+    double *nq_ray;
+    double *nq_w;
     double *res_t;              // nearest hit of each path ray: Distance,
     int2 *res_hit;              //   (object code or -1, list position)
     HitHead *hit_head;          // hit queue the shadow and shade stages read
@@ -722,6 +728,10 @@ __device__ __forceinline__ void pixel_of_index(const FrameParams &fp, const WfBu
     inside = X < fp.width && local_y < fp.local_rows && Y < fp.height;
 }
 
+__device__ __forceinline__ double path_weight_of_index(const WfBuf &wf, bool first, unsigned int i)
+{
+    return first ? 1.0 : __ldcs(wf.q_w + i);
+}
 __device__ __forceinline__ void path_ray_of_index(const FrameParams &fp, const WfBuf &wf, bool first, unsigned int i,
                                                   d3 &O, d3 &D, int &pid, bool &valid)
 {
@@ -914,19 +924,83 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
 __device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc(m & ((1u << lane) - 1u)); }
 
 __device__ __forceinline__ void write_hit(HitHead *heads, HitTail *tails, size_t s, d3 P, d3 N, d3 D, int obj, int order,
-                                          int pid)
+                                          int pid, double W)
 {
     HitHead hh;
     HitTail ht;
     hh.P[0] = P.x; hh.P[1] = P.y; hh.P[2] = P.z; hh.obj = obj; hh.order = order;
     ht.N[0] = N.x; ht.N[1] = N.y; ht.N[2] = N.z; ht.pid = pid; ht.pad0 = 0;
-    ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.pad1 = 0.0;
+    ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.W = W;
     const uint4 *sh = reinterpret_cast<const uint4 *>(&hh);
     const uint4 *st = reinterpret_cast<const uint4 *>(&ht);
     uint4 *dh = reinterpret_cast<uint4 *>(heads + s);
     uint4 *dt = reinterpret_cast<uint4 *>(tails + s);
     dh[0] = sh[0]; dh[1] = sh[1];
     dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+}
+
+// The reflection ray of a hit (erl:216-224): leaves the hit location along the bounced direction and carries the
+// path's weight times (number of lights * reflectivity) — what the reference's fold adds L times over (erl:239-247).
+// A path ends at the depth limit, at a surface that reflects nothing, and when its weight is zero.  Every lane of the
+// warp calls this; `hit` says whether the lane has one.
+__device__ __forceinline__ void emit_next_rays(const DevScene &sc, const FrameParams &fp, const WfBuf &wf, int bounce,
+                                               unsigned int *ctr, int lane, bool hit, d3 P, d3 N, d3 D, int obj, int pid, double W)
+{
+    bool cont = false;
+    double refl = 0.0;
+    if (hit && bounce + 1 < fp.depth) {
+        refl = reflectivity_of(sc, obj);
+        cont = !(refl == 0.0 || W == 0.0);
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, cont);
+    if (!m) return;
+    unsigned int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(ctr + WF_NNEXT, (unsigned int)__popc(m));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (cont) {
+        const size_t np = (size_t)wf.n_pad;
+        const size_t s = slot0 + rank_in(m, lane);
+        const d3 nd = vbounce(D, N);                                  // erl:219-221
+        wf.nq_pid[s] = pid;
+        wf.nq_w[s] = W * ((double)sc.n_lights * refl);
+        double *q = wf.nq_ray + s;
+        q[0] = P.x; q[np] = P.y; q[2 * np] = P.z;
+        q[3 * np] = nd.x; q[4 * np] = nd.y; q[5 * np] = nd.z;
+    }
+}
+
+// The path kernels' own emission: hit records and reflection rays of up to 32 hits with ONE atomic (the counters of
+// the hit queue and of the next path queue are neighbours: a 64-bit add reserves both ranges).  Every lane calls.
+static_assert(WF_NHITS == 0 && WF_NNEXT == 1, "one 64-bit add reserves hits (low word) and next rays (high word)");
+__device__ __forceinline__ void emit_hits_and_rays(const DevScene &sc, const FrameParams &fp, const WfBuf &wf, int bounce,
+                                                   unsigned int *ctr, int lane, bool hit, d3 P, d3 N, d3 D, int obj,
+                                                   int order, int pid, double W)
+{
+    const unsigned int mh = __ballot_sync(0xffffffffu, hit);
+    if (!mh) return;
+    bool cont = false;
+    double refl = 0.0;
+    if (hit && bounce + 1 < fp.depth) {
+        refl = reflectivity_of(sc, obj);
+        cont = !(refl == 0.0 || W == 0.0);
+    }
+    const unsigned int mc = __ballot_sync(0xffffffffu, cont);
+    unsigned long long old = 0;
+    if (lane == 0)
+        old = atomicAdd(reinterpret_cast<unsigned long long *>(ctr + WF_NHITS),
+                        (unsigned long long)__popc(mh) | ((unsigned long long)__popc(mc) << 32));
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (hit) write_hit(wf.hit_head, wf.hit_tail, (size_t)(unsigned int)old + rank_in(mh, lane), P, N, D, obj, order, pid, W);
+    if (cont) {
+        const size_t np = (size_t)wf.n_pad;
+        const size_t s = (size_t)(old >> 32) + rank_in(mc, lane);
+        const d3 nd = vbounce(D, N);                                  // erl:219-221
+        wf.nq_pid[s] = pid;
+        wf.nq_w[s] = W * ((double)sc.n_lights * refl);
+        double *q = wf.nq_ray + s;
+        q[0] = P.x; q[np] = P.y; q[2 * np] = P.z;
+        q[3 * np] = nd.x; q[4 * np] = nd.y; q[5 * np] = nd.z;
+    }
 }
 
 // Work distribution of the traversal kernels.  A warp owns a chunk of kWfChunk consecutive
@@ -1059,18 +1133,16 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                 }
             } else {
                 const bool hit = valid && best.obj >= 0;
-                const unsigned int m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    unsigned int slot0 = 0;
-                    if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)__popc(m));
-                    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                    if (hit) {
-                        const d3 O = ray.O(), D = ray.D();
-                        const d3 P = vadd(O, vscale(D, best.t));      // erl:384-387 / 443-447 / 471-475
-                        const d3 N = hit_normal(sc, best.obj, P);
-                        write_hit(wf.hit_head, wf.hit_tail, slot0 + rank_in(m, lane), P, N, D, best.obj, best.order, pid);
-                    }
+                d3 P = mk(0, 0, 0), N = P, D = P;
+                double W = 0.0;
+                if (hit) {
+                    const d3 O = ray.O();
+                    D = ray.D();
+                    P = vadd(O, vscale(D, best.t));                   // erl:384-387 / 443-447 / 471-475
+                    N = hit_normal(sc, best.obj, P);
+                    W = path_weight_of_index(wf, FIRST, i);
                 }
+                emit_hits_and_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, best.obj, best.order, pid, W);
             }
         }
     }
@@ -1132,18 +1204,23 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
     // turns the first `take` queued hits into hit records, one per lane (erl:384-390, 443-451, 471-476)
     auto emit_finished = [&](int take) {
         __syncwarp();
-        unsigned int slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(ctr + WF_NHITS, (unsigned int)take);
-        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-        if (lane < take) {
-            const FinishedHit fh = fin[lane];
-            d3 O, D;
-            int pid;
-            bool valid;
-            path_ray_of_index(fp, wf, false, fh.idx, O, D, pid, valid);
-            const d3 P = vadd(O, vscale(D, fh.t));
-            const d3 N = hit_normal(sc, fh.obj, P);
-            write_hit(wf.hit_head, wf.hit_tail, slot0 + lane, P, N, D, fh.obj, object_order(sc, fh.obj), pid);
+        {
+            const bool hit = lane < take;
+            d3 P = mk(0, 0, 0), N = P, D = P;
+            double W = 0.0;
+            int pid = 0, obj = -1, order = 0;
+            if (hit) {
+                const FinishedHit fh = fin[lane];
+                d3 O;
+                bool valid;
+                path_ray_of_index(fp, wf, false, fh.idx, O, D, pid, valid);
+                obj = fh.obj;
+                order = object_order(sc, obj);
+                P = vadd(O, vscale(D, fh.t));
+                N = hit_normal(sc, obj, P);
+                W = path_weight_of_index(wf, false, fh.idx);
+            }
+            emit_hits_and_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, obj, order, pid, W);
         }
         __syncwarp();
         FinishedHit keep;
@@ -1286,23 +1363,28 @@ wf_emit_hits(const __grid_constant__ DevScene sc, const __grid_constant__ FrameP
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
 #pragma unroll
         for (int k = 0; k < kEmitBatches; k++) {
-            if (r[k].x >= 0) {
+            const bool hit = r[k].x >= 0;
+            d3 P = mk(0, 0, 0), N = P, D = P;
+            double W = 0.0;
+            int pid = 0;
+            if (hit) {
                 const unsigned int i = (unsigned int)base + (unsigned int)(32 * k + lane);
-                d3 O, D;
-                int pid;
+                d3 O;
                 bool valid;
                 path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
                 double t = wf.res_t[i];
-                d3 P = vadd(O, vscale(D, t));                         // erl:384-387 / 443-447 / 471-475
-                d3 N = hit_normal(sc, r[k].x, P);
+                P = vadd(O, vscale(D, t));                            // erl:384-387 / 443-447 / 471-475
+                N = hit_normal(sc, r[k].x, P);
+                W = path_weight_of_index(wf, FIRST, i);
                 size_t s = slot0 + rank_in(m[k], lane);
-                write_hit(out_head, out_tail, s, P, N, D, r[k].x, r[k].y, pid);
+                write_hit(out_head, out_tail, s, P, N, D, r[k].x, r[k].y, pid, W);
                 if constexpr (SORT) {
                     unsigned int key = sort_cell(sc, P);
                     wf.r_key[s] = key;
                     atomicAdd(wf.hist + key, 1u);
                 }
             }
+            if (m[k]) emit_next_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, r[k].x, pid, W);
             slot0 += __popc(m[k]);
         }
     }
@@ -1448,8 +1530,8 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
-// Folds the lights of every hit of one bounce (erl:209-252 in forward form, see pix_consume)
-// and emits the reflection rays of the next bounce.
+// Folds the lights of every hit of one bounce into the pixel's colour (erl:209-252 in forward form, see
+// pix_consume).  The reflection rays of the next bounce were emitted with the hits (emit_next_rays).
 __global__ void __launch_bounds__(kWfThreads, ERT_SHADE_MINBLOCKS)
 wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
          const __grid_constant__ WfBuf wf, int bounce)
@@ -1464,7 +1546,6 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
     for (unsigned long long base = (unsigned long long)warp * 32; base < n_hits; base += (unsigned long long)n_warps * 32) {
         size_t h = (size_t)base + lane;
         bool valid = h < n_hits;
-        bool cont = false;
         int pid = 0;
         d3 P = mk(0, 0, 0), N = P, D = P;
         if (valid) {
@@ -1488,30 +1569,9 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
                 if (wf.lit[(size_t)l * np + h]) S = vadd(S, light_term(sc.lights + 9 * (size_t)l, mat, P, N, D));
             }
             d3 Cold = mk(0.0, 0.0, 0.0);
-            double Wold = 1.0;
-            if (bounce > 0) {
-                Cold = mk(wf.C[pid], wf.C[np + pid], wf.C[2 * np + pid]);
-                Wold = wf.W[pid];
-            }
-            d3 Cnew = vadd(Cold, vscale(S, Wold));
+            if (bounce > 0) Cold = mk(wf.C[pid], wf.C[np + pid], wf.C[2 * np + pid]);
+            const d3 Cnew = vadd(Cold, vscale(S, ht.W));
             wf.C[pid] = Cnew.x; wf.C[np + pid] = Cnew.y; wf.C[2 * np + pid] = Cnew.z;
-            double refl = mat[5];
-            cont = !(bounce + 1 >= fp.depth || refl == 0.0 || Wold == 0.0);
-            if (cont) wf.W[pid] = Wold * ((double)L * refl);
-        }
-        unsigned int m = __ballot_sync(0xffffffffu, cont);
-        if (m) {
-            unsigned int slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(ctr + WF_NNEXT, (unsigned int)__popc(m));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (cont) {
-                size_t s = slot0 + rank_in(m, lane);
-                d3 nd = vbounce(D, N);                            // erl:219-221
-                wf.q_pid[s] = pid;
-                double *q = wf.q_ray + s;
-                q[0] = P.x; q[np] = P.y; q[2 * np] = P.z;
-                q[3 * np] = nd.x; q[4 * np] = nd.y; q[5 * np] = nd.z;
-            }
         }
     }
 }

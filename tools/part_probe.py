@@ -36,7 +36,7 @@ def main():
     dev.close()
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "split"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("split", "flush")):
     main()
 
 
@@ -75,3 +75,28 @@ def split_probe():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "split":
     split_probe()
+
+
+def flush_probe():
+    """One part of N with and without the L2 flush between frames."""
+    wl = sys.argv[2] if len(sys.argv) > 2 else "c4"
+    w, h, depth = 3840, 2160, 5
+    flat = sc.synthetic_scene(wl)
+    dev = flat.upload(0)
+    for n_parts in (1, 8):
+        band = multigpu.default_band_rows(h, n_parts)
+        for flush in (True, False):
+            ms = []
+            for i in range(12):
+                if flush:
+                    _lib.l2_flush(0)
+                dev.render_async(w, h, depth, slot=0, fmt="rgb8", accel="auto", band_rows=band, n_parts=n_parts, part=0)
+                dev.wait(0)
+                if i >= 2:
+                    ms.append(dev.stats(0)["kernel_ms"])
+            print("%s part 0 of %d, L2 %s: kernel_ms median %.3f min %.3f" % (wl, n_parts, "flushed" if flush else "as the last frame left it", float(np.median(ms)), min(ms)))
+    dev.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "flush":
+    flush_probe()
