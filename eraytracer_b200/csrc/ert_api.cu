@@ -280,13 +280,8 @@ int flatten(const ert_scene_desc *d, HostScene &h)
     // exception in any of them (std::bad_alloc, std::system_error) comes back through join() below.
     WorkerGroup builders;
     {
-        // tuning knobs of the BVH builder (defaults are the measured best, DESIGN.md "BVH")
-        int leaf_max = kBvhLeafMax;
-        float trav_cost = kBvhTravCost;
-        if (const char *e = getenv("ERT_BVH_LEAF_MAX")) leaf_max = atoi(e);
-        if (const char *e = getenv("ERT_BVH_TRAV_COST")) trav_cost = (float)atof(e);
-        builders.spawn([&h, &centers, &radii, leaf_max, trav_cost] {
-            build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, leaf_max, trav_cost);
+        builders.spawn([&h, &centers, &radii] {
+            build_sphere_bvh(centers.data(), radii.data(), h.n_spheres, h.bvh, kBvhLeafMax, kBvhTravCost);
         });
     }
     if (h.n_spheres > 0) {
@@ -488,7 +483,6 @@ int upload_scene(ert_scene *s)
             CU(cudaFuncGetAttributes(&fa, fn));
             size_t need = (size_t)blocks_per_sm * (fa.sharedSizeBytes + 1024);      // 1 KB per block is reserved
             int pct = (int)((need * 100 + prop.sharedMemPerMultiprocessor - 1) / prop.sharedMemPerMultiprocessor) + 1;
-            if (const char *e = getenv("ERT_WF_CARVEOUT")) pct = atoi(e);
             CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(pct, 100)));
             return ERT_OK;
         };
@@ -738,12 +732,10 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     // Binning hits by location pays when shadow rays walk the BVH (coherent warps); with a direction
     // grid for every light it costs more than the path rays gain from it (measured on C4: 29.2 vs 27.8 ms).
     static const bool force_sort = getenv("ERT_WF_SORT") != nullptr;
-    // experiments: first bounce whose path rays use the cell grid / the refilling form of that kernel
-    static const int cells_from = getenv("ERT_CELLS_FROM") ? atoi(getenv("ERT_CELLS_FROM")) : 0;
-    static const int cells_refill_from = getenv("ERT_CELLS_REFILL_FROM") ? atoi(getenv("ERT_CELLS_REFILL_FROM")) : ERT_WF_REFILL_FROM;
+    constexpr int cells_from = 0;                                  // first bounce whose path rays use the cell grid
+    constexpr int cells_refill_from = ERT_WF_REFILL_FROM;          // ... and the refilling form of that kernel
     const bool shadows_walk = !no_grid ? d.lg_count < d.n_lights : true;
-    static const bool env_no_sort = getenv("ERT_WF_NO_SORT") != nullptr;
-    const bool no_sort = unsorted || (!shadows_walk && !force_sort) || env_no_sort;
+    const bool no_sort = unsorted || (!shadows_walk && !force_sort);
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -791,12 +783,11 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             CU(cudaStreamSynchronize(st));
             if (sl.wf_ctr_host[WF_NNEXT] == 0) break;
         }
-        static const bool refill_no_emit = getenv("ERT_REFILL_NO_EMIT") != nullptr;      // A/B: hit emission as its own launch
         const bool sort = b >= 1 && !no_sort && !scan;
         const bool grid_b = cells && b >= cells_from;
         const bool refill = b >= (grid_b ? cells_refill_from : ERT_WF_REFILL_FROM);
         // the path kernels emit their hit records themselves unless the hits are to be binned first
-        const bool emitted = !scan && (b == 0 || (!sort && !(refill && refill_no_emit)));
+        const bool emitted = !scan && (b == 0 || !sort);
         if (scan) {
             // planes/triangles seed every ray's result (counted with the other kernels), then every ray meets every sphere
             if (b == 0) wf_scan_init<false, true, COUNT><<<s->wf_grid[3], 256, 0, st>>>(d, fp, wf, b);

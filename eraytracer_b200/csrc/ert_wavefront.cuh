@@ -34,11 +34,6 @@
 #endif
 
 namespace ert {
-#ifdef ERT_FILTER_OLD
-#define GRID_EXACT_FN grid_exact_old
-#else
-#define GRID_EXACT_FN grid_exact
-#endif
 
 // One hit of a path ray, in two records: the shadow stage streams only the 32-byte heads
 // (dense, every fetched byte used), the shade stage reads both.
@@ -441,63 +436,6 @@ __device__ __forceinline__ float grid_advance(GridWalk &g, const GridRay &r, con
 // instead of one at a time.  A sphere is listed in every cell it overlaps, so the incumbent itself
 // comes by again: it is skipped.  Once the incumbent has improved inside the cell the remaining
 // survivors go through the filter's distance cull again before their FP64 test.
-#ifdef ERT_FILTER_OLD
-template <bool COUNT>
-__device__ __forceinline__ unsigned int grid_filter_old(const DevScene &sc, const SRay &f, int first, int cnt, float cullk,
-                                                    Tally<COUNT> &tl)
-{
-    const float4 *fp4 = sc.cg.ref_filter + first;
-    unsigned int surv = 0u;
-    float4 s0 = __ldg(fp4), s1 = __ldg(fp4 + min(1, cnt - 1));
-#pragma unroll 1
-    for (int k = 0; k < cnt; k += 2) {
-        // two spheres per round, the next two already in flight
-        const float4 n0 = __ldg(fp4 + min(k + 2, cnt - 1)), n1 = __ldg(fp4 + min(k + 3, cnt - 1));
-        float b, v;
-        if constexpr (COUNT) tl.filter += (k + 1 < cnt) ? 2 : 1;
-        if (filter_stage1(f, s0, b, v)) {
-            if (filter_stage2(f, s0, b, v, cullk)) surv |= 1u << k;
-        }
-        if (filter_stage1(f, s1, b, v) && k + 1 < cnt) {
-            if (filter_stage2(f, s1, b, v, cullk)) surv |= 2u << k;
-        }
-        s0 = n0; s1 = n1;
-    }
-    return surv;
-}
-
-template <bool COUNT>
-__device__ __forceinline__ void grid_exact_old(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
-                                           unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
-{
-    const DevScene::CellGridDev &cg = sc.cg;
-    bool improved = false;
-    while (surv) {
-        const int k = __ffs((int)surv) - 1;
-        surv &= surv - 1u;
-        const int slot = first + k;
-        const int sph = __ldg(cg.ref_sph + slot);
-        const int code = obj_code(OBJ_SPHERE, sph);
-        if (code == skip_obj || code == best.obj) continue;
-        if (improved) {
-            const float4 fs = __ldg(cg.ref_filter + slot);
-            float b, v;
-            if (!filter_stage1(f, fs, b, v) || !filter_stage2(f, fs, b, v, cullk)) continue;
-        }
-        double t;
-        TALLY(exact_sph);
-        if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
-            const int ord = sc.sph_order[sph];
-            if (better(t, ord, best)) {
-                best.t = t; best.order = ord; best.obj = code;
-                cullk = cullk_from(f, ray.inv_sqrt_a(), best);
-                improved = true;
-            }
-        }
-    }
-}
-
-#endif
 template <bool COUNT>
 __device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SRay &f, int first, int cnt, Tally<COUNT> &tl)
 {
@@ -585,20 +523,11 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
     int cnt = (int)(c & 127u);
     while (cnt > 32) {
         // rare: more than one mask's worth of spheres in the cell; all but the last 32 are finished here
-#ifdef ERT_FILTER_OLD
-        const unsigned int sv = grid_filter_old<COUNT>(sc, f, first, 32, g.cullk, tl);
-        grid_exact_old<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
-#else
         const unsigned int sv = grid_filter<COUNT>(sc, f, first, 32, tl);
         grid_exact<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
-#endif
         first += 32; cnt -= 32;
     }
-#ifdef ERT_FILTER_OLD
-    surv = grid_filter_old<COUNT>(sc, f, first, cnt, g.cullk, tl);
-#else
     surv = grid_filter<COUNT>(sc, f, first, cnt, tl);
-#endif
     return true;
 }
 __device__ __forceinline__ bool grid_leave(GridWalk &g, float te)
@@ -616,7 +545,7 @@ __device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const D
     int first;
     float te;
     if (!grid_find<COUNT>(g, r, sc, ray, f, best, skip_obj, tl, surv, first, te)) return true;
-    GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
+    grid_exact<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
     return grid_leave(g, te);
 }
 
@@ -1121,7 +1050,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     bool found = false;
                     if (walking) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, skip, tl, surv, first, te);
                     __syncwarp();
-                    if (surv) GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
+                    if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
                     if (walking) walking = found ? !grid_leave(gw, te) : false;
                 }
             }
@@ -1293,7 +1222,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                 bool found = false;
                 if (have) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, -1, tl, surv, first, te);
                 __syncwarp();
-                if (surv) GRID_EXACT_FN<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
+                if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
                 if (have) over = found ? grid_leave(gw, te) : true;
             } else {
                 if (have) over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
