@@ -112,7 +112,7 @@ struct Slot {
 
 struct ert_scene {
     int device = 0;
-    int wf_grid[6] = {0, 0, 0, 0, 0, 0};   // persistent grid sizes: path(first), path, shadow, shade, cell-grid path(first), path
+    int wf_grid[7] = {0, 0, 0, 0, 0, 0, 0};   // persistent grid sizes: path(first), path, shadow, shade, cell-grid path(first), path, shadow+shade
     int wf_grid_scan = 0;              // brute-force scan kernels (2 blocks per SM)
     HostScene host;
     DevScene dev{};
@@ -475,6 +475,8 @@ int upload_scene(ert_scene *s)
         s->wf_grid[2] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shade, kWfThreads, 0));
         s->wf_grid[3] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_shadow_shade<false>, kWfThreads, 0));
+        s->wf_grid[6] = prop.multiProcessorCount * std::max(nb, 1);
         // The walks live on L1 (tree nodes + the local-memory stacks).  Ask for exactly the shared memory
         // the resident blocks need, so that the rest of the 256 KB array serves as L1 (measured on C4:
         // 23.5 -> 23.1 ms against the driver's default split; too small a carve-out halves the occupancy).
@@ -736,6 +738,9 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     constexpr int cells_refill_from = ERT_WF_REFILL_FROM;          // ... and the refilling form of that kernel
     const bool shadows_walk = !no_grid ? d.lg_count < d.n_lights : true;
     const bool no_sort = unsorted || (!shadows_walk && !force_sort);
+    // every light has a direction grid and the hits stay in arrival order: shadow rays and the light fold in one kernel
+    static const bool env_no_fuse = getenv("ERT_WF_NO_FUSE") != nullptr;
+    const bool fused_shade = !env_no_fuse && !scan && !shadows_walk && no_sort && d.n_lights <= 32;
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -848,6 +853,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             TICK(2);
             wf_scan<true, false, COUNT><<<s->wf_grid_scan, kScanThreads, kScanSmem, st2>>>(d, fps, wf, b);
         }
+        else if (fused_shade) wf_shadow_shade<COUNT><<<s->wf_grid[6], kWfThreads, 0, st2>>>(d, fps, wf, b);
         else if (no_grid) wf_trace_shadow<COUNT, false><<<s->wf_grid[2], kWfThreads, 0, st2>>>(d, fps, wf, b);
         else wf_trace_shadow<COUNT, true><<<s->wf_grid[2], kWfThreads, 0, st2>>>(d, fps, wf, b);
         TICK(1);
@@ -856,10 +862,13 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
             wf_scan_finish<true, false><<<s->wf_grid[3], 256, 0, st2>>>(d, wf, b);
             n++;
         }
-        wf_shade<<<s->wf_grid[3], kWfThreads, 0, st2>>>(d, fp, wf, b);
+        if (!fused_shade) {
+            wf_shade<<<s->wf_grid[3], kWfThreads, 0, st2>>>(d, fp, wf, b);
+            n++;
+        }
         if (overlap) CU(cudaEventRecord(sl.ev_shade[(size_t)b], st2));
         last_shaded = b;
-        n += 2;
+        n++;
         TICK(2);
         WF_CHECK("wf_shade");
     }
@@ -895,6 +904,11 @@ int finish_slot(ert_scene *s, Slot &sl)
     sl.stats.exact_sphere_tests = c0[CNT_EXACT_SPH] + c1[CNT_EXACT_SPH];
     sl.stats.exact_other_tests = c0[CNT_EXACT_OTHER] + c1[CNT_EXACT_OTHER];
     sl.stats.cell_steps = c0[CNT_CELL] + c1[CNT_CELL];
+#ifdef ERT_PROBE
+    fprintf(stderr, "PROBE path rays %llu filter %llu exact %llu cell %llu :", c0[CNT_RAYS], c0[CNT_FILTER], c0[CNT_EXACT_SPH], c0[CNT_CELL]);
+    for (int k = 0; k < 8; k++) fprintf(stderr, " p%d=%llu", k, c0[CNT_PROBE + k]);
+    fprintf(stderr, "\n");
+#endif
     sl.stats.bounces_recorded = sl.wf_levels;
     for (int b = 0; b < sl.wf_levels; b++) {
         const unsigned int *c = sl.wf_ctr_all_host + (size_t)b * kWfCtr;

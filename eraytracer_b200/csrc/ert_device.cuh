@@ -104,7 +104,11 @@ struct FrameParams {
     unsigned long long *counters;
 };
 
+#ifdef ERT_PROBE
+enum Counter : int { CNT_RAYS = 0, CNT_FILTER = 1, CNT_BOX = 2, CNT_EXACT_SPH = 3, CNT_EXACT_OTHER = 4, CNT_CELL = 5, CNT_PROBE = 8, CNT_N = 16 };
+#else
 enum Counter : int { CNT_RAYS = 0, CNT_FILTER = 1, CNT_BOX = 2, CNT_EXACT_SPH = 3, CNT_EXACT_OTHER = 4, CNT_CELL = 5, CNT_N = 8 };
+#endif
 constexpr int kCounterSets = 2;      // [0]: megakernels and wf_trace_path*, [1]: wf_trace_shadow
 
 // ------------------------------------------------------------------ FP64 literal algebra
@@ -205,10 +209,18 @@ __device__ __forceinline__ bool triangle_exact(d3 O, d3 D, const double *tr, dou
 template <bool COUNT>
 struct Tally {
     unsigned int filter = 0, box = 0, exact_sph = 0, exact_other = 0, cell = 0;
+#ifdef ERT_PROBE
+    unsigned int p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 };
 template <>
 struct Tally<false> {};
 #define TALLY(field) do { if constexpr (COUNT) tl.field++; } while (0)
+#ifdef ERT_PROBE
+#define PROBE(k, n) do { if constexpr (COUNT) tl.p[k] += (n); } while (0)
+#else
+#define PROBE(k, n) do { } while (0)
+#endif
 
 // planes and triangles (erl:353-356): always FP64, list order kept through `order`
 template <bool COUNT>
@@ -735,6 +747,12 @@ __device__ __forceinline__ void flush_counters(const FrameParams &fp, int rays, 
             if (c) atomicAdd(fp.counters + CNT_EXACT_SPH, (unsigned long long)c);
             if (d) atomicAdd(fp.counters + CNT_EXACT_OTHER, (unsigned long long)d);
         }
+#ifdef ERT_PROBE
+        for (int k = 0; k < 8; k++) {
+            unsigned int q = __reduce_add_sync(0xffffffffu, tl.p[k]);
+            if ((threadIdx.x & 31) == 0 && q) atomicAdd(fp.counters + CNT_PROBE + k, (unsigned long long)q);
+        }
+#endif
     }
 }
 

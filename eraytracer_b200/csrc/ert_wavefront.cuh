@@ -469,6 +469,8 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
                                            unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
+    PROBE(0, surv ? 1 : 0);
+    PROBE(1, __popc(surv));
     while (surv) {
         const int k = __ffs((int)surv) - 1;
         surv &= surv - 1u;
@@ -476,18 +478,23 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
         const int sph = __ldg(cg.ref_sph + slot);
         if (sph < 0) continue;                           // padding (only a NaN ray gets here)
         const int code = obj_code(OBJ_SPHERE, sph);
-        if (code == skip_obj || code == best.obj) continue;
+        if (code == skip_obj || code == best.obj) { PROBE(2, 1); continue; }
         {
             const float4 fs = __ldg(cg.ref_filter + slot);
             float b, v;
             filter_stage1(f, fs, b, v);
+#ifdef ERT_PROBE
+            if (b < -f.bcull) PROBE(3, 1); else if (!filter_stage2(f, fs, b, v, cullk)) PROBE(4, 1);
+#endif
             if (!filter_stage2(f, fs, b, v, cullk)) continue;
         }
         double t;
         TALLY(exact_sph);
         if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
             const int ord = sc.sph_order[sph];
+            PROBE(5, 1);
             if (better(t, ord, best)) {
+                PROBE(6, 1);
                 best.t = t; best.order = ord; best.obj = code;
                 cullk = cullk_from(f, ray.inv_sqrt_a(), best);
             }
@@ -1020,6 +1027,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                             // scan, so the minimum over (t, order) is unchanged
                             double t;
                             TALLY(exact_sph);
+                            PROBE(7, 1);
                             if (sphere_exact(O, D, a, sc.sph_exact[hint], t)) {
                                 int ord = sc.sph_order[hint];
                                 if (better(t, ord, best)) {
@@ -1503,6 +1511,93 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
             wf.C[pid] = Cnew.x; wf.C[np + pid] = Cnew.y; wf.C[2 * np + pid] = Cnew.z;
         }
     }
+}
+
+// shadow_factor/4 and the light fold in ONE pass over the hits, for scenes whose lights all have a direction grid
+// (no walk, no per-warp occluder ring).  A lane keeps one hit and asks its lights one after the other, so the warp
+// still works in one direction grid at a time; the hit location and the target's sphere are fetched once instead
+// of once per light, the shadow factors never travel through HBM, and the colour update follows at once
+// (erl:209-252 in forward form, exactly wf_shade's arithmetic).
+#ifndef ERT_SS_MINBLOCKS
+#define ERT_SS_MINBLOCKS 4
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(kWfThreads, ERT_SS_MINBLOCKS)
+wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
+                const __grid_constant__ WfBuf wf, int bounce)
+{
+    unsigned int *ctr = wf.ctr + bounce * kWfCtr;
+    const unsigned int n_hits = ctr[WF_NHITS];
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_SHADOW);
+    const int lane = threadIdx.x & 31;
+    const size_t np = (size_t)wf.n_pad;
+    const int L = sc.n_lights;
+    Tally<COUNT> tl;
+    unsigned int rays = 0;
+    unsigned long long begin, end;
+    while (next_chunk(cursor, (unsigned long long)n_hits, lane, begin, end)) {
+        for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
+            const unsigned long long j = b0 + lane;
+            const bool valid = j < end;
+            const unsigned int h = valid ? (unsigned int)j : (unsigned int)(end - 1);
+            const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+            const d3 P = mk(r0.x, r0.y, r0.z);
+            const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
+            const int order = (int)(__double_as_longlong(r0.w) >> 32);
+            // on their way to L1 while the first direction is normalised
+            if (obj_type(target) == OBJ_SPHERE) prefetch_l1(sc.sph_exact + obj_index(target));
+            unsigned int litmask = 0u;
+            for (int l = 0; l < L; l++) {
+                __syncwarp();
+                if (!valid) continue;
+                rays++;
+                const double *lt = sc.lights + 9 * (size_t)l;
+                const d3 O = mk(lt[3], lt[4], lt[5]);
+                const d3 D = vnormalize(vsub(P, O));                   // erl:257-260
+                const double a = D.x * D.x + D.y * D.y + D.z * D.z;
+                double t;
+                // "nearest == Object" (erl:263) <=> Object is hit and nothing beats its (t, order)
+                if (!object_exact(sc, target, O, D, a, t)) continue;
+                Hit best;
+                best.t = t; best.order = order; best.obj = target;
+                scan_others_shadow<COUNT>(sc, O, D, best, target, tl);
+                bool lit = best.obj == target;
+                if (lit && sc.n_spheres > 0) {
+                    SRay f;
+                    double a2, inv;
+                    make_sray(sc, O, D, f, a2, inv);
+                    lit = !light_grid_occluded<COUNT>(sc, sc.lgrids[l], f, O, D, a, inv, best, target, tl);
+                }
+                if (lit) litmask |= 1u << l;
+            }
+            __syncwarp();
+            // A hit no light reaches adds S * W = (0,0,0) * W to its pixel: the colour buffer starts at +0.0 and a sum
+            // that starts there is never -0.0, so for any finite W the addition changes no bit and the record's tail
+            // stays unread.  (A non-finite W needs a reflectivity beyond 1e60: BEAM floats cannot hold the products
+            // the reference would form with it, erl:239-247 raises badarith long before.)
+            if (valid && litmask) {
+                HitTail ht;
+                {
+                    const uint4 *st = reinterpret_cast<const uint4 *>(wf.hit_tail + h);
+                    uint4 *dt = reinterpret_cast<uint4 *>(&ht);
+                    dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+                }
+                const int pid = ht.pid;
+                d3 S = mk(0.0, 0.0, 0.0);
+                const d3 N = mk(ht.N[0], ht.N[1], ht.N[2]);
+                const d3 Dp = mk(ht.D[0], ht.D[1], ht.D[2]);
+                const double *mat = material_ptr(sc, target);
+                for (int l = 0; l < L; l++) {
+                    if (litmask & (1u << l)) S = vadd(S, light_term(sc.lights + 9 * (size_t)l, mat, P, N, Dp));
+                }
+                d3 Cold = mk(0.0, 0.0, 0.0);
+                if (bounce > 0) Cold = mk(wf.C[pid], wf.C[np + pid], wf.C[2 * np + pid]);
+                const d3 Cnew = vadd(Cold, vscale(S, ht.W));
+                wf.C[pid] = Cnew.x; wf.C[np + pid] = Cnew.y; wf.C[2 * np + pid] = Cnew.z;
+            }
+        }
+    }
+    flush_counters<COUNT>(fp, (int)rays, tl);
 }
 
 __global__ void __launch_bounds__(kWfThreads)

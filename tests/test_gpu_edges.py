@@ -348,7 +348,9 @@ def test_wavefront_binned_queues_render_the_same_frame(gpu):
     e, se = dev.render(w, h, depth, fmt="f64", accel="bvh")
     assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, e)
     assert sa["rays"] == sb["rays"] == sc_["rays"] == se["rays"]
-    assert sa["gpu_launches"] > sb["gpu_launches"] == se["gpu_launches"] > sc_["gpu_launches"] == 1
+    # binned > arrival order with separate shadow and shade launches > shadow rays and light fold in one launch
+    # (every light has a direction grid) > one megakernel
+    assert sa["gpu_launches"] > sb["gpu_launches"] > se["gpu_launches"] > sc_["gpu_launches"] == 1
     # instrumented run: same frame, counters filled
     d, sd = dev.render(w, h, depth, fmt="f64", accel="bvh", flags=_lib.FLAG_COUNT_TESTS)
     assert np.array_equal(a, d) and sd["box_tests"] > 0 and sd["sphere_filter_tests"] > 0
