@@ -21,9 +21,21 @@ constexpr int kCellGridMinSpheres = 256;     // smaller scenes do not get one
 constexpr int kCellGridMaxRes = 1024;        // cells per axis (the walk keeps plane indices as floats)
 constexpr int kCellGridMaxCount = 127;       // spheres per cell (7 bits of the packed cell word)
 constexpr int kCellGridPad = 4;              // a cell's list is stored in whole groups of this many entries
+constexpr int kCellGridInline = 6;           // spheres held inside a cell's own 128-byte block (what the device walks)
 constexpr uint32_t kCellGridMaxRefs = 1u << 25;
 constexpr int kCellGridBigCells = 512;       // a sphere overlapping more cells than this goes to the `big` list
 constexpr int kCellGridMaxBig = 32;          // more of those than this: no grid for the scene
+
+// What the device walks: one 128-byte block per cell, its address pure arithmetic on the cell id (no dependent
+// fetch between the 3-D DDA and the spheres), holding the first kCellGridInline filter spheres and their indices.
+// Longer lists continue in over_filter / over_sph from entry `more` on, in whole groups of kCellGridPad.
+struct alignas(16) CellBlock {
+    float f[kCellGridInline][4];              // filter spheres (padding: R = -3e38, never passes)
+    int32_t sph[kCellGridInline];             // sphere indices (padding: -1)
+    uint32_t cnt;                             // spheres listed in the cell, inline ones included
+    uint32_t more;                            // first overflow entry of this cell
+};
+static_assert(sizeof(CellBlock) == 128, "one cell is one 128-byte line");
 
 struct CellGrid {
     bool enabled = false;
@@ -35,7 +47,14 @@ struct CellGrid {
     std::vector<float> ref_filter;                // [n_refs][4] filter spheres in cell order (padding: R = -3e38)
     std::vector<int32_t> ref_sph;                 // [n_refs] sphere index (padding: -1)
     std::vector<int32_t> big;                     // spheres tested by every ray
+    // the same lists in the layout the device walks (pack_cell_blocks); cells / ref_* above stay on the host
+    std::vector<CellBlock> blocks;                // [rx*ry*rz]
+    std::vector<float> over_filter;               // [n_over][4]
+    std::vector<int32_t> over_sph;                // [n_over]
 };
+
+// Fills blocks / over_* from cells / ref_* (called by build_cell_grid; separate so that the tests can check it).
+void pack_cell_blocks(CellGrid &g);
 
 // centers: n*3, radii: n, filter: n*4 (the scene's FP32 filter spheres), abs_max: largest
 // |coordinate| of any sphere box.  Leaves out.enabled false when the scene does not suit a grid.

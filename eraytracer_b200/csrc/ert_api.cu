@@ -424,12 +424,13 @@ int upload_scene(ert_scene *s)
     }
     {
         const CellGrid &G = h.cgrid;
-        const unsigned int *cells; const float *rf; const int *rs; const int *big;
-        if ((rc = upload<unsigned int>(s, G.cells, &cells)) != ERT_OK) return rc;
-        if ((rc = upload<float>(s, G.ref_filter, &rf)) != ERT_OK) return rc;
-        if ((rc = upload<int>(s, G.ref_sph, &rs)) != ERT_OK) return rc;
+        const CellBlock *blocks; const float *rf; const int *rs; const int *big;
+        if ((rc = upload<CellBlock>(s, G.blocks, &blocks)) != ERT_OK) return rc;
+        if ((rc = upload<float>(s, G.over_filter, &rf)) != ERT_OK) return rc;
+        if ((rc = upload<int>(s, G.over_sph, &rs)) != ERT_OK) return rc;
         if ((rc = upload<int>(s, G.big, &big)) != ERT_OK) return rc;
-        d.cg.cells = cells; d.cg.ref_filter = reinterpret_cast<const float4 *>(rf); d.cg.ref_sph = rs; d.cg.big = big;
+        d.cg.blocks = reinterpret_cast<const uint4 *>(blocks); d.cg.over_filter = reinterpret_cast<const float4 *>(rf);
+        d.cg.over_sph = rs; d.cg.big = big;
         d.cg.n_big = (int)G.big.size(); d.cg.enabled = G.enabled ? 1 : 0;
         d.cg.rx = G.res[0]; d.cg.ry = G.res[1]; d.cg.rz = G.res[2];
         for (int a = 0; a < 3; a++) { d.cg.lo[a] = G.lo[a]; d.cg.hi[a] = G.hi[a]; }

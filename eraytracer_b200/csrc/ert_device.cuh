@@ -65,9 +65,9 @@ struct DevScene {
     int lg_count;
     // uniform cell grid over the spheres (cell_grid.h): path-ray candidates by 3-D DDA
     struct CellGridDev {
-        const unsigned int *cells;   // [rx*ry*rz] (first_ref << 7) | count
-        const float4 *ref_filter;    // filter spheres in cell order
-        const int *ref_sph;          // ref slot -> sphere index
+        const uint4 *blocks;         // [rx*ry*rz] 128-byte CellBlock (cell_grid.h): 6 filter spheres, 6 indices, count, overflow
+        const float4 *over_filter;   // filter spheres of the lists longer than a block, in groups of four
+        const int *over_sph;         // overflow entry -> sphere index
         const int *big;              // spheres every ray tests (too large for the cells)
         int n_big, enabled;
         int rx, ry, rz;

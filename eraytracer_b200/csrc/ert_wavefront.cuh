@@ -368,17 +368,22 @@ struct GridRay {
 struct GridWalk {
     float nbx, nby, nbz;             // index of the next plane along each axis (integer-valued)
     float tx, ty, tz;                // ray parameter there
-    int id;                          // linear cell id; < 0: the walk is over
-    unsigned int c;                  // packed word of cell `id` (fetched one step ahead)
+    int id;                          // linear id of the cell the walk looks at next; < 0: the walk is over
     float cullk;
 };
+constexpr int kOrderUnknown = INT_MIN;          // Hit::order of a sphere whose list position has not been fetched yet
+
+// list position of the incumbent (the grid walk fetches it only when a tie asks for it)
+__device__ __forceinline__ int hit_order(const DevScene &sc, const Hit &best)
+{
+    return best.order != kOrderUnknown ? best.order : object_order(sc, best.obj);
+}
 
 __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevScene &sc, const SRay &f, float cullk)
 {
     const DevScene::CellGridDev &cg = sc.cg;
     g.cullk = cullk;
     g.id = -1;
-    g.c = 0u;
     float t0;
     if (!slab_test(f, cg.lo[0], cg.hi[0], cg.lo[1], cg.hi[1], cg.lo[2], cg.hi[2], cullk, t0)) return;
     const float inv_cs = 1.0f / cg.cs;
@@ -400,7 +405,6 @@ __device__ __forceinline__ void grid_start(GridWalk &g, GridRay &r, const DevSce
     const int sy = cg.rx, sz = cg.rx * cg.ry;
     r.sgn = (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
     g.id = (int)cx + sy * (int)cy + sz * (int)cz;
-    g.c = __ldg(cg.cells + g.id);
 }
 
 // Moves the walk to the next cell (id < 0 when that is outside the grid) and returns the ray
@@ -430,70 +434,85 @@ __device__ __forceinline__ float grid_advance(GridWalk &g, const GridRay &r, con
     return te;
 }
 
-// The spheres listed in one cell, in two phases.  grid_filter runs the FP32 filter over up to 32 of
-// them (survivors as a bit mask), grid_exact the literal FP64 tests of the survivors: callers put the
-// second phase where the lanes of a warp meet again, so that they enter the expensive part together
-// instead of one at a time.  A sphere is listed in every cell it overlaps, so the incumbent itself
-// comes by again: it is skipped.  Once the incumbent has improved inside the cell the remaining
-// survivors go through the filter's distance cull again before their FP64 test.
-template <bool COUNT>
-__device__ __forceinline__ unsigned int grid_filter(const DevScene &sc, const SRay &f, int first, int cnt, Tally<COUNT> &tl)
+// The spheres listed in one cell, in two phases.  The filter phase runs stage 1 of the FP32 filter and the
+// behind-the-origin cull over up to 32 of them (survivors as a bit mask: bits 0-5 the spheres inside the cell's
+// block, bits 6.. the overflow entries from `obase` on), grid_exact the literal FP64 tests of the survivors: callers
+// put the second phase where the lanes of a warp meet again, so that they enter the expensive part together
+// instead of one at a time.  A sphere is listed in every cell it overlaps, so the incumbent itself comes by again:
+// it is skipped.  The beyond-the-incumbent cull waits for grid_exact, where it sees the newest cull distance.
+// (The sphere a reflected ray leaves passes stage 1 in every cell that lists it — the origin lies on it — and was
+// a third of all survivors before the behind-the-origin cull moved into the mask.)
+__device__ __forceinline__ unsigned int stage1_bit(const SRay &f, float4 s, float nth, float nbc)
 {
-    // Stage 1 only, four spheres per round and no branch inside: the lists are stored in whole groups of four
-    // (kCellGridPad; the padding never passes), the pass bits go into the survivor mask with selects.  Stage 2
-    // (behind the origin / beyond the incumbent) waits for grid_exact, where it sees the newest cull distance.
-    static_assert(kCellGridPad == 4, "the filter loop reads groups of four");
-    const float4 *fp4 = sc.cg.ref_filter + first;
-    const float nth = -f.theta;
+    float b, v;
+    filter_stage1(f, s, b, v);
+    return (v < nth || b < nbc) ? 0u : 1u;
+}
+constexpr int kGridOverChunk = 24;               // overflow entries per survivor mask (bits 6..29)
+static_assert(kCellGridInline == 6 && kCellGridPad == 4 && kGridOverChunk % kCellGridPad == 0, "mask layout");
+
+// stage 1 over `cnt` overflow entries from `e0` on (whole groups of four; the padding never passes)
+__device__ __forceinline__ unsigned int grid_filter_over(const DevScene &sc, const SRay &f, unsigned int e0, int cnt)
+{
+    const float4 *fp4 = sc.cg.over_filter + e0;
+    const float nth = -f.theta, nbc = -f.bcull;
     unsigned int surv = 0u;
     float4 s0 = __ldg(fp4), s1 = __ldg(fp4 + 1), s2 = __ldg(fp4 + 2), s3 = __ldg(fp4 + 3);
 #pragma unroll 1
     for (int k = 0; k < cnt; k += 4) {
         // the next group is in flight while this one is tested (one group past the list at the end: it exists)
         const float4 n0 = __ldg(fp4 + k + 4), n1 = __ldg(fp4 + k + 5), n2 = __ldg(fp4 + k + 6), n3 = __ldg(fp4 + k + 7);
-        float b, v0, v1, v2, v3;
-        filter_stage1(f, s0, b, v0);
-        filter_stage1(f, s1, b, v1);
-        filter_stage1(f, s2, b, v2);
-        filter_stage1(f, s3, b, v3);
-        const unsigned int m = (v0 < nth ? 0u : 1u) | (v1 < nth ? 0u : 2u) | (v2 < nth ? 0u : 4u) | (v3 < nth ? 0u : 8u);
-        surv |= m << k;
+        const unsigned int m = stage1_bit(f, s0, nth, nbc) | (stage1_bit(f, s1, nth, nbc) << 1) |
+                               (stage1_bit(f, s2, nth, nbc) << 2) | (stage1_bit(f, s3, nth, nbc) << 3);
+        surv |= m << (kCellGridInline + k);
         s0 = n0; s1 = n1; s2 = n2; s3 = n3;
     }
-    if constexpr (COUNT) tl.filter += cnt;
     return surv;
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, const RaySlot &ray, int first,
-                                           unsigned int surv, int skip_obj, Hit &best, float &cullk, Tally<COUNT> &tl)
+__device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, const RaySlot &ray, int cell,
+                                           unsigned int obase, unsigned int surv, int skip_obj, Hit &best, float &cullk,
+                                           Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
+    const uint4 *blk = cg.blocks + (size_t)cell * 8;
     PROBE(0, surv ? 1 : 0);
     PROBE(1, __popc(surv));
     while (surv) {
         const int k = __ffs((int)surv) - 1;
         surv &= surv - 1u;
-        const int slot = first + k;
-        const int sph = __ldg(cg.ref_sph + slot);
+        int sph;
+        float4 fs;
+        if (k < kCellGridInline) {
+            sph = __ldg(reinterpret_cast<const int *>(blk) + 4 * kCellGridInline + k);
+            fs = __ldg(reinterpret_cast<const float4 *>(blk) + k);
+        } else {
+            const unsigned int e = obase + (unsigned int)(k - kCellGridInline);
+            sph = __ldg(cg.over_sph + e);
+            fs = __ldg(cg.over_filter + e);
+        }
         if (sph < 0) continue;                           // padding (only a NaN ray gets here)
         const int code = obj_code(OBJ_SPHERE, sph);
         if (code == skip_obj || code == best.obj) { PROBE(2, 1); continue; }
         {
-            const float4 fs = __ldg(cg.ref_filter + slot);
             float b, v;
             filter_stage1(f, fs, b, v);
-#ifdef ERT_PROBE
-            if (b < -f.bcull) PROBE(3, 1); else if (!filter_stage2(f, fs, b, v, cullk)) PROBE(4, 1);
-#endif
-            if (!filter_stage2(f, fs, b, v, cullk)) continue;
+            if (!filter_stage2(f, fs, b, v, cullk)) { PROBE(4, 1); continue; }
         }
         double t;
         TALLY(exact_sph);
         if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
-            const int ord = sc.sph_order[sph];
             PROBE(5, 1);
-            if (better(t, ord, best)) {
+            // better() of erl:319 with the list positions fetched only for a tie
+            bool win = best.obj < 0 || t < best.t;
+            int ord = kOrderUnknown;
+            if (!win && t == best.t) {
+                ord = sc.sph_order[sph];
+                best.order = hit_order(sc, best);
+                win = ord < best.order;
+            }
+            if (win) {
                 PROBE(6, 1);
                 best.t = t; best.order = ord; best.obj = code;
                 cullk = cullk_from(f, ray.inv_sqrt_a(), best);
@@ -503,38 +522,58 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
 }
 
 // Runs empty cells until the ray holds a cell with spheres and filters those (while-while, like
-// trav_step).  The word of the next cell is fetched before the current one is looked at, so its
-// latency overlaps the step arithmetic and the sphere tests.  Returns false when the walk is over
-// (the next cell starts beyond the cull distance, or outside the grid); otherwise `surv` marks the
-// filter survivors among the spheres from slot `first` on and `te` is where the cell ends:
-// grid_exact on the survivors and grid_leave complete the step.
+// trav_step).  A cell's block sits at an address the DDA computes, so the block of the NEXT cell is
+// asked for (prefetch to L1) as soon as the step arithmetic has its id: its latency overlaps the
+// sphere tests of this cell.  Returns false when the walk is over (the next cell starts beyond the
+// cull distance, or outside the grid); otherwise `surv` marks the filter survivors of cell `cell`
+// (overflow entries counted from `obase`) and `te` is where the cell ends: grid_exact on the
+// survivors and grid_leave complete the step.
 template <bool COUNT>
 __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
                                           const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl, unsigned int &surv,
-                                          int &first, float &te)
+                                          int &cell, unsigned int &obase, float &te)
 {
     const DevScene::CellGridDev &cg = sc.cg;
-    unsigned int c;
     surv = 0u;
+    const uint4 *blk;
+    uint2 hd;
+    float4 s0, s1, s2, s3, s4, s5;
     for (;;) {
         if (g.id < 0) return false;
         WF_ASSERT(g.id < cg.rx * cg.ry * cg.rz, "cell %d of %d", g.id, cg.rx * cg.ry * cg.rz);
-        c = g.c;
+        cell = g.id;
+        blk = cg.blocks + (size_t)cell * 8;
+        // one 128-byte line: count and overflow word, six filter spheres
+        hd = __ldg(reinterpret_cast<const uint2 *>(blk) + 15);
+        s0 = __ldg(reinterpret_cast<const float4 *>(blk));
+        s1 = __ldg(reinterpret_cast<const float4 *>(blk) + 1);
+        s2 = __ldg(reinterpret_cast<const float4 *>(blk) + 2);
+        s3 = __ldg(reinterpret_cast<const float4 *>(blk) + 3);
+        s4 = __ldg(reinterpret_cast<const float4 *>(blk) + 4);
+        s5 = __ldg(reinterpret_cast<const float4 *>(blk) + 5);
         TALLY(cell);
         te = grid_advance(g, r, cg);
-        g.c = g.id >= 0 ? __ldg(cg.cells + g.id) : 0u;
-        if (c & 127u) break;
+        if (g.id >= 0 && !(te > g.cullk)) prefetch_l1(cg.blocks + (size_t)g.id * 8);
+        if (hd.x) break;
         if (te > g.cullk) { g.id = -1; return false; }
     }
-    first = (int)(c >> 7);
-    int cnt = (int)(c & 127u);
-    while (cnt > 32) {
-        // rare: more than one mask's worth of spheres in the cell; all but the last 32 are finished here
-        const unsigned int sv = grid_filter<COUNT>(sc, f, first, 32, tl);
-        grid_exact<COUNT>(sc, f, ray, first, sv, skip_obj, best, g.cullk, tl);
-        first += 32; cnt -= 32;
+    const float nth = -f.theta, nbc = -f.bcull;
+    int cnt = (int)hd.x;
+    obase = hd.y;
+    if constexpr (COUNT) tl.filter += cnt;
+    surv = stage1_bit(f, s0, nth, nbc) | (stage1_bit(f, s1, nth, nbc) << 1) | (stage1_bit(f, s2, nth, nbc) << 2) |
+           (stage1_bit(f, s3, nth, nbc) << 3) | (stage1_bit(f, s4, nth, nbc) << 4) | (stage1_bit(f, s5, nth, nbc) << 5);
+    cnt -= kCellGridInline;
+    if (cnt > 0) {
+        while (cnt > kGridOverChunk) {
+            // rare: more than one mask's worth of spheres in the cell; all but the last chunk are finished here
+            const unsigned int sv = surv | grid_filter_over(sc, f, obase, kGridOverChunk);
+            grid_exact<COUNT>(sc, f, ray, cell, obase, sv, skip_obj, best, g.cullk, tl);
+            surv = 0u;
+            obase += kGridOverChunk; cnt -= kGridOverChunk;
+        }
+        surv |= grid_filter_over(sc, f, obase, cnt);
     }
-    surv = grid_filter<COUNT>(sc, f, first, cnt, tl);
     return true;
 }
 __device__ __forceinline__ bool grid_leave(GridWalk &g, float te)
@@ -548,11 +587,11 @@ template <bool COUNT>
 __device__ __forceinline__ bool grid_step(GridWalk &g, const GridRay &r, const DevScene &sc, const RaySlot &ray,
                                           const SRay &f, Hit &best, int skip_obj, Tally<COUNT> &tl)
 {
-    unsigned int surv;
-    int first;
+    unsigned int surv, obase;
+    int cell;
     float te;
-    if (!grid_find<COUNT>(g, r, sc, ray, f, best, skip_obj, tl, surv, first, te)) return true;
-    grid_exact<COUNT>(sc, f, ray, first, surv, skip_obj, best, g.cullk, tl);
+    if (!grid_find<COUNT>(g, r, sc, ray, f, best, skip_obj, tl, surv, cell, obase, te)) return true;
+    grid_exact<COUNT>(sc, f, ray, cell, obase, surv, skip_obj, best, g.cullk, tl);
     return grid_leave(g, te);
 }
 
@@ -613,6 +652,7 @@ __device__ __forceinline__ void grid_trace(const DevScene &sc, const RaySlot &ra
     GridRay r;
     if (!grid_begin<COUNT>(g, r, sc, ray, f, inv_sqrt_a, skip_obj, best, tl)) return;
     while (!grid_step<COUNT>(g, r, sc, ray, f, best, skip_obj, tl)) { }
+    best.order = hit_order(sc, best);
 }
 
 // one ray through the cell grid, no persistence (ert_trace_rays with ERT_ACCEL_GRID)
@@ -1052,20 +1092,20 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                 // the lanes of the batch walk to their next cell with spheres and filter them on their own,
                 // then meet for the FP64 tests of the survivors
                 while (__any_sync(0xffffffffu, walking)) {
-                    unsigned int surv = 0u;
-                    int first = 0;
+                    unsigned int surv = 0u, obase = 0u;
+                    int cell = 0;
                     float te = 0.f;
                     bool found = false;
-                    if (walking) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, skip, tl, surv, first, te);
+                    if (walking) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, skip, tl, surv, cell, obase, te);
                     __syncwarp();
-                    if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, skip, best, gw.cullk, tl);
+                    if (surv) grid_exact<COUNT>(sc, f, ray, cell, obase, surv, skip, best, gw.cullk, tl);
                     if (walking) walking = found ? !grid_leave(gw, te) : false;
                 }
             }
             if (searched && best.obj >= 0 && obj_type(best.obj) == OBJ_SPHERE) hint = obj_index(best.obj);
             if constexpr (!EMIT) {
                 if (in_range) {
-                    __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, best.order));
+                    __stcs(wf.res_hit + i, make_int2(valid ? best.obj : -1, hit_order(sc, best)));
                     __stcs(wf.res_t + i, best.t);
                 }
             } else {
@@ -1079,7 +1119,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     N = hit_normal(sc, best.obj, P);
                     W = path_weight_of_index(wf, FIRST, i);
                 }
-                emit_hits_and_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, best.obj, best.order, pid, W);
+                emit_hits_and_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, best.obj, hit ? hit_order(sc, best) : 0, pid, W);
             }
         }
     }
@@ -1224,13 +1264,13 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
             if constexpr (GRID) {
                 // the lanes walk to their next cell with spheres and filter them on their own, then meet
                 // for the FP64 tests of the survivors
-                unsigned int surv = 0u;
-                int first = 0;
+                unsigned int surv = 0u, obase = 0u;
+                int cell = 0;
                 float te = 0.f;
                 bool found = false;
-                if (have) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, -1, tl, surv, first, te);
+                if (have) found = grid_find<COUNT>(gw, gr, sc, ray, f, best, -1, tl, surv, cell, obase, te);
                 __syncwarp();
-                if (surv) grid_exact<COUNT>(sc, f, ray, first, surv, -1, best, gw.cullk, tl);
+                if (surv) grid_exact<COUNT>(sc, f, ray, cell, obase, surv, -1, best, gw.cullk, tl);
                 if (have) over = found ? grid_leave(gw, te) : true;
             } else {
                 if (have) over = trav_step<false, COUNT>(tr, stack, sc, ray, f, best, -1, -1, tl);
@@ -1249,7 +1289,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                 }
                 if (over) have = false;
             } else if (over) {
-                __stcs(wf.res_hit + idx, make_int2(best.obj, best.order));
+                __stcs(wf.res_hit + idx, make_int2(best.obj, hit_order(sc, best)));
                 __stcs(wf.res_t + idx, best.t);
                 have = false;
             }

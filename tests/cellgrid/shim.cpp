@@ -40,6 +40,12 @@ long long cg_n_big(void *p) { return (long long)((CellGrid *)p)->big.size(); }
 const unsigned int *cg_cells(void *p) { return ((CellGrid *)p)->cells.data(); }
 const int *cg_ref_sph(void *p) { return ((CellGrid *)p)->ref_sph.data(); }
 const int *cg_big(void *p) { return ((CellGrid *)p)->big.data(); }
+// the layout the device walks (pack_cell_blocks): 128-byte blocks + overflow arrays
+const void *cg_blocks(void *p) { return ((CellGrid *)p)->blocks.data(); }
+long long cg_n_over(void *p) { return (long long)((CellGrid *)p)->over_sph.size(); }
+const int *cg_over_sph(void *p) { return ((CellGrid *)p)->over_sph.data(); }
+const float *cg_over_filter(void *p) { return ((CellGrid *)p)->over_filter.data(); }
+const float *cg_ref_filter(void *p) { return ((CellGrid *)p)->ref_filter.data(); }
 
 // The device walk for the ray (O, D), no incumbent.  Writes up to `cap` visited cell ids and the
 // ray parameter (filter space: |d| = 1 + 2^-19) at which each was entered; returns the number of

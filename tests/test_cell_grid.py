@@ -33,10 +33,10 @@ def cg():
     L.cg_free.argtypes = [vp]
     L.cg_enabled.argtypes = [vp]
     L.cg_geometry.argtypes = [vp, vp, vp, vp, vp]
-    for name in ("cg_n_cells", "cg_n_refs", "cg_n_big"):
+    for name in ("cg_n_cells", "cg_n_refs", "cg_n_big", "cg_n_over"):
         getattr(L, name).restype = ctypes.c_longlong
         getattr(L, name).argtypes = [vp]
-    for name in ("cg_cells", "cg_ref_sph", "cg_big"):
+    for name in ("cg_cells", "cg_ref_sph", "cg_big", "cg_blocks", "cg_over_sph", "cg_over_filter", "cg_ref_filter"):
         getattr(L, name).restype = vp
         getattr(L, name).argtypes = [vp]
     L.cg_walk.restype = ctypes.c_longlong
@@ -292,6 +292,48 @@ def test_walk_is_complete_awkward_scenes(cg, case):
     rays = np.concatenate([rand_rays(rng, 500, lo, hi),
                            rand_rays(rng, 150, [3 * v - 50 for v in lo], [3 * v + 50 for v in hi])])
     check_complete(g, rays, min_touch=50)
+    g.close()
+
+
+@pytest.mark.parametrize("density", [0.2, 0.35, 2.0])
+def test_packed_blocks_hold_the_same_lists(cg, density):
+    """The device walks 128-byte blocks (6 spheres inside, longer lists in overflow groups of four): every cell's
+    block and overflow range must decode to exactly the list the completeness tests above check."""
+    rng = np.random.default_rng(11)
+    c, r = rand_scene(rng, 4000, (40, 16, 40), 0.2, 1.2)
+    g = Grid(cg, c, r, density=density)
+    assert g.enabled
+    L = cg
+    n_cells, n_over, n_refs = len(g.cells), L.cg_n_over(g.h), L.cg_n_refs(g.h)
+    blocks = np.ctypeslib.as_array(ctypes.cast(L.cg_blocks(g.h), ctypes.POINTER(ctypes.c_uint32)), (n_cells, 32)).copy()
+    over_sph = np.ctypeslib.as_array(ctypes.cast(L.cg_over_sph(g.h), ctypes.POINTER(ctypes.c_int32)), (n_over,)).copy()
+    over_f = np.ctypeslib.as_array(ctypes.cast(L.cg_over_filter(g.h), ctypes.POINTER(ctypes.c_float)), (n_over, 4)).copy()
+    ref_f = np.ctypeslib.as_array(ctypes.cast(L.cg_ref_filter(g.h), ctypes.POINTER(ctypes.c_float)), (n_refs, 4)).copy()
+    assert n_over % 4 == 0 and n_over >= 4
+    longest = 0
+    for cell in range(n_cells):
+        word = int(g.cells[cell])
+        first, cnt = word >> 7, word & 127
+        b = blocks[cell]
+        f_in = b[:24].view(np.float32).reshape(6, 4)
+        s_in = b[24:30].view(np.int32)
+        assert int(b[30]) == cnt
+        more = int(b[31])
+        n_in = min(cnt, 6)
+        assert np.array_equal(s_in[:n_in], g.ref_sph[first:first + n_in])
+        assert np.array_equal(f_in[:n_in], ref_f[first:first + n_in])
+        assert np.all(s_in[n_in:] == -1) and np.all(f_in[n_in:, 3] < -1e38)          # padding never passes
+        if cnt > 6:
+            n_ov = cnt - 6
+            assert more % 4 == 0 and more + (n_ov + 3) // 4 * 4 + 4 <= n_over          # one group past the list exists
+            assert np.array_equal(over_sph[more:more + n_ov], g.ref_sph[first + 6:first + cnt])
+            assert np.array_equal(over_f[more:more + n_ov], ref_f[first + 6:first + cnt])
+            pad = (n_ov + 3) // 4 * 4
+            assert np.all(over_sph[more + n_ov:more + pad] == -1) and np.all(over_f[more + n_ov:more + pad, 3] < -1e38)
+        longest = max(longest, cnt)
+    assert np.all(over_sph[-4:] == -1)
+    if density <= 0.35:
+        assert longest > 6                                           # the overflow path is exercised
     g.close()
 
 
