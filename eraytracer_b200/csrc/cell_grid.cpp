@@ -73,7 +73,7 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
         if ((double)out.res[a] * (double)out.cs < ext[a]) return;
         n_cells *= (size_t)out.res[a];
     }
-    if (n_cells > ((size_t)1 << 24)) return;           // 128 bytes per cell on the device
+    if (n_cells > ((size_t)1 << 23)) return;           // 256 bytes per cell on the device
 
     // pass 1: counts
     std::vector<uint32_t> count(n_cells, 0);
@@ -152,13 +152,18 @@ void build_cell_grid(const double *centers, const double *radii, const float *fi
 void pack_cell_blocks(CellGrid &g)
 {
     const size_t n_cells = g.cells.size();
-    g.blocks.assign(n_cells, CellBlock());
-    size_t n_over = 0;
-    for (size_t c = 0; c < n_cells; c++) {
-        const uint32_t cnt = g.cells[c] & 127u;
-        if (cnt > (uint32_t)kCellGridInline)
-            n_over += ((size_t)cnt - kCellGridInline + kCellGridPad - 1) / kCellGridPad * kCellGridPad;
+    constexpr uint32_t kIn = (uint32_t)(kCellGridInline * kCellGridBlocks);
+    CellBlock empty;
+    for (int k = 0; k < kCellGridInline; k++) {
+        empty.f[k][0] = empty.f[k][1] = empty.f[k][2] = 0.f;
+        empty.f[k][3] = -3.0e38f;
+        empty.sph[k] = -1;
     }
+    empty.cnt = 0; empty.more = 0;
+    g.blocks.assign(n_cells * kCellGridBlocks, empty);
+    auto padded = [](uint32_t cnt) { return cnt > kIn ? ((size_t)(cnt - kIn) + kCellGridPad - 1) / kCellGridPad * kCellGridPad : 0; };
+    size_t n_over = 0;
+    for (size_t c = 0; c < n_cells; c++) n_over += padded(g.cells[c] & 127u);
     n_over += kCellGridPad;                          // the walk's loop may fetch one group past the last list
     g.over_filter.assign(n_over * 4, 0.f);
     for (size_t k = 0; k < n_over; k++) g.over_filter[k * 4 + 3] = -3.0e38f;
@@ -166,27 +171,22 @@ void pack_cell_blocks(CellGrid &g)
     size_t run = 0;
     for (size_t c = 0; c < n_cells; c++) {
         const uint32_t cnt = g.cells[c] & 127u, first = g.cells[c] >> 7;
-        CellBlock &b = g.blocks[c];
-        for (int k = 0; k < kCellGridInline; k++) {
-            b.f[k][0] = b.f[k][1] = b.f[k][2] = 0.f;
-            b.f[k][3] = -3.0e38f;
-            b.sph[k] = -1;
-        }
-        b.cnt = cnt;
-        b.more = (uint32_t)run;
+        CellBlock *b = &g.blocks[c * kCellGridBlocks];
+        b[0].cnt = cnt;
+        b[0].more = (uint32_t)run;
         for (uint32_t k = 0; k < cnt; k++) {
             const size_t slot = (size_t)first + k;
-            if (k < (uint32_t)kCellGridInline) {
-                memcpy(b.f[k], &g.ref_filter[slot * 4], 16);
-                b.sph[k] = g.ref_sph[slot];
+            if (k < kIn) {
+                CellBlock &bb = b[k / kCellGridInline];
+                memcpy(bb.f[k % kCellGridInline], &g.ref_filter[slot * 4], 16);
+                bb.sph[k % kCellGridInline] = g.ref_sph[slot];
             } else {
-                const size_t o = run + (k - kCellGridInline);
+                const size_t o = run + (k - kIn);
                 memcpy(&g.over_filter[o * 4], &g.ref_filter[slot * 4], 16);
                 g.over_sph[o] = g.ref_sph[slot];
             }
         }
-        if (cnt > (uint32_t)kCellGridInline)
-            run += ((size_t)cnt - kCellGridInline + kCellGridPad - 1) / kCellGridPad * kCellGridPad;
+        run += padded(cnt);
     }
 }
 

@@ -21,14 +21,16 @@ constexpr int kCellGridMinSpheres = 256;     // smaller scenes do not get one
 constexpr int kCellGridMaxRes = 1024;        // cells per axis (the walk keeps plane indices as floats)
 constexpr int kCellGridMaxCount = 127;       // spheres per cell (7 bits of the packed cell word)
 constexpr int kCellGridPad = 4;              // a cell's list is stored in whole groups of this many entries
-constexpr int kCellGridInline = 6;           // spheres held inside a cell's own 128-byte block (what the device walks)
+constexpr int kCellGridInline = 6;           // spheres held in one 128-byte block (what the device walks)
+constexpr int kCellGridBlocks = 2;           // blocks per cell: lists of up to 12 spheres need no dependent fetch
 constexpr uint32_t kCellGridMaxRefs = 1u << 25;
 constexpr int kCellGridBigCells = 512;       // a sphere overlapping more cells than this goes to the `big` list
 constexpr int kCellGridMaxBig = 32;          // more of those than this: no grid for the scene
 
-// What the device walks: one 128-byte block per cell, its address pure arithmetic on the cell id (no dependent
-// fetch between the 3-D DDA and the spheres), holding the first kCellGridInline filter spheres and their indices.
-// Longer lists continue in over_filter / over_sph from entry `more` on, in whole groups of kCellGridPad.
+// What the device walks: kCellGridBlocks 128-byte blocks per cell, their address pure arithmetic on the cell id (no
+// dependent fetch between the 3-D DDA and the spheres), each holding kCellGridInline filter spheres and their
+// indices; a list that fits the first block leaves the second untouched.  Longer lists continue in over_filter /
+// over_sph from entry `more` on, in whole groups of kCellGridPad.  `cnt` and `more` are those of the first block.
 struct alignas(16) CellBlock {
     float f[kCellGridInline][4];              // filter spheres (padding: R = -3e38, never passes)
     int32_t sph[kCellGridInline];             // sphere indices (padding: -1)
@@ -48,7 +50,7 @@ struct CellGrid {
     std::vector<int32_t> ref_sph;                 // [n_refs] sphere index (padding: -1)
     std::vector<int32_t> big;                     // spheres tested by every ray
     // the same lists in the layout the device walks (pack_cell_blocks); cells / ref_* above stay on the host
-    std::vector<CellBlock> blocks;                // [rx*ry*rz]
+    std::vector<CellBlock> blocks;                // [rx*ry*rz][kCellGridBlocks]
     std::vector<float> over_filter;               // [n_over][4]
     std::vector<int32_t> over_sph;                // [n_over]
 };

@@ -65,7 +65,7 @@ struct DevScene {
     int lg_count;
     // uniform cell grid over the spheres (cell_grid.h): path-ray candidates by 3-D DDA
     struct CellGridDev {
-        const uint4 *blocks;         // [rx*ry*rz] 128-byte CellBlock (cell_grid.h): 6 filter spheres, 6 indices, count, overflow
+        const uint4 *blocks;         // [rx*ry*rz][2] 128-byte CellBlock (cell_grid.h): 6 filter spheres, 6 indices, count, overflow
         const float4 *over_filter;   // filter spheres of the lists longer than a block, in groups of four
         const int *over_sph;         // overflow entry -> sphere index
         const int *big;              // spheres every ray tests (too large for the cells)

@@ -448,8 +448,11 @@ __device__ __forceinline__ unsigned int stage1_bit(const SRay &f, float4 s, floa
     filter_stage1(f, s, b, v);
     return (v < nth || b < nbc) ? 0u : 1u;
 }
-constexpr int kGridOverChunk = 24;               // overflow entries per survivor mask (bits 6..29)
-static_assert(kCellGridInline == 6 && kCellGridPad == 4 && kGridOverChunk % kCellGridPad == 0, "mask layout");
+constexpr int kGridInline = kCellGridInline * kCellGridBlocks;      // mask bits 0..11: the spheres in the cell's two blocks
+constexpr int kGridOverChunk = 20;                                  // overflow entries per survivor mask (bits 12..31)
+constexpr int kBlockU4 = 8 * kCellGridBlocks;                       // uint4 per cell
+static_assert(kCellGridInline == 6 && kCellGridBlocks == 2 && kCellGridPad == 4 && kGridOverChunk % kCellGridPad == 0 &&
+              kGridInline + kGridOverChunk <= 32, "mask layout");
 
 // stage 1 over `cnt` overflow entries from `e0` on (whole groups of four; the padding never passes)
 __device__ __forceinline__ unsigned int grid_filter_over(const DevScene &sc, const SRay &f, unsigned int e0, int cnt)
@@ -464,7 +467,7 @@ __device__ __forceinline__ unsigned int grid_filter_over(const DevScene &sc, con
         const float4 n0 = __ldg(fp4 + k + 4), n1 = __ldg(fp4 + k + 5), n2 = __ldg(fp4 + k + 6), n3 = __ldg(fp4 + k + 7);
         const unsigned int m = stage1_bit(f, s0, nth, nbc) | (stage1_bit(f, s1, nth, nbc) << 1) |
                                (stage1_bit(f, s2, nth, nbc) << 2) | (stage1_bit(f, s3, nth, nbc) << 3);
-        surv |= m << (kCellGridInline + k);
+        surv |= m << (kGridInline + k);
         s0 = n0; s1 = n1; s2 = n2; s3 = n3;
     }
     return surv;
@@ -476,7 +479,7 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
                                            Tally<COUNT> &tl)
 {
     const DevScene::CellGridDev &cg = sc.cg;
-    const uint4 *blk = cg.blocks + (size_t)cell * 8;
+    const uint4 *blk = cg.blocks + (size_t)cell * kBlockU4;
     PROBE(0, surv ? 1 : 0);
     PROBE(1, __popc(surv));
     while (surv) {
@@ -484,11 +487,12 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
         surv &= surv - 1u;
         int sph;
         float4 fs;
-        if (k < kCellGridInline) {
-            sph = __ldg(reinterpret_cast<const int *>(blk) + 4 * kCellGridInline + k);
-            fs = __ldg(reinterpret_cast<const float4 *>(blk) + k);
+        if (k < kGridInline) {
+            const int half = k >= kCellGridInline ? 1 : 0, j = k - half * kCellGridInline;
+            sph = __ldg(reinterpret_cast<const int *>(blk + 8 * half) + 4 * kCellGridInline + j);
+            fs = __ldg(reinterpret_cast<const float4 *>(blk + 8 * half) + j);
         } else {
-            const unsigned int e = obase + (unsigned int)(k - kCellGridInline);
+            const unsigned int e = obase + (unsigned int)(k - kGridInline);
             sph = __ldg(cg.over_sph + e);
             fs = __ldg(cg.over_filter + e);
         }
@@ -542,7 +546,7 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         if (g.id < 0) return false;
         WF_ASSERT(g.id < cg.rx * cg.ry * cg.rz, "cell %d of %d", g.id, cg.rx * cg.ry * cg.rz);
         cell = g.id;
-        blk = cg.blocks + (size_t)cell * 8;
+        blk = cg.blocks + (size_t)cell * kBlockU4;
         // one 128-byte line: count and overflow word, six filter spheres
         hd = __ldg(reinterpret_cast<const uint2 *>(blk) + 15);
         s0 = __ldg(reinterpret_cast<const float4 *>(blk));
@@ -553,7 +557,10 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         s5 = __ldg(reinterpret_cast<const float4 *>(blk) + 5);
         TALLY(cell);
         te = grid_advance(g, r, cg);
-        if (g.id >= 0 && !(te > g.cullk)) prefetch_l1(cg.blocks + (size_t)g.id * 8);
+        if (g.id >= 0 && !(te > g.cullk)) {
+            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
+            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4 + 8);
+        }
         if (hd.x) break;
         if (te > g.cullk) { g.id = -1; return false; }
     }
@@ -563,16 +570,27 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
     if constexpr (COUNT) tl.filter += cnt;
     surv = stage1_bit(f, s0, nth, nbc) | (stage1_bit(f, s1, nth, nbc) << 1) | (stage1_bit(f, s2, nth, nbc) << 2) |
            (stage1_bit(f, s3, nth, nbc) << 3) | (stage1_bit(f, s4, nth, nbc) << 4) | (stage1_bit(f, s5, nth, nbc) << 5);
-    cnt -= kCellGridInline;
-    if (cnt > 0) {
-        while (cnt > kGridOverChunk) {
-            // rare: more than one mask's worth of spheres in the cell; all but the last chunk are finished here
-            const unsigned int sv = surv | grid_filter_over(sc, f, obase, kGridOverChunk);
-            grid_exact<COUNT>(sc, f, ray, cell, obase, sv, skip_obj, best, g.cullk, tl);
-            surv = 0u;
-            obase += kGridOverChunk; cnt -= kGridOverChunk;
+    if (cnt > kCellGridInline) {
+        // the second block of the cell (asked for a step ago, like the first)
+        s0 = __ldg(reinterpret_cast<const float4 *>(blk) + 8);
+        s1 = __ldg(reinterpret_cast<const float4 *>(blk) + 9);
+        s2 = __ldg(reinterpret_cast<const float4 *>(blk) + 10);
+        s3 = __ldg(reinterpret_cast<const float4 *>(blk) + 11);
+        s4 = __ldg(reinterpret_cast<const float4 *>(blk) + 12);
+        s5 = __ldg(reinterpret_cast<const float4 *>(blk) + 13);
+        surv |= (stage1_bit(f, s0, nth, nbc) << 6) | (stage1_bit(f, s1, nth, nbc) << 7) | (stage1_bit(f, s2, nth, nbc) << 8) |
+                (stage1_bit(f, s3, nth, nbc) << 9) | (stage1_bit(f, s4, nth, nbc) << 10) | (stage1_bit(f, s5, nth, nbc) << 11);
+        cnt -= kGridInline;
+        if (cnt > 0) {
+            while (cnt > kGridOverChunk) {
+                // rare: more than one mask's worth of spheres in the cell; all but the last chunk are finished here
+                const unsigned int sv = surv | grid_filter_over(sc, f, obase, kGridOverChunk);
+                grid_exact<COUNT>(sc, f, ray, cell, obase, sv, skip_obj, best, g.cullk, tl);
+                surv = 0u;
+                obase += kGridOverChunk; cnt -= kGridOverChunk;
+            }
+            surv |= grid_filter_over(sc, f, obase, cnt);
         }
-        surv |= grid_filter_over(sc, f, obase, cnt);
     }
     return true;
 }
@@ -1016,6 +1034,26 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
     return true;
 }
 
+// A warp that has taken the chunk [begin, end) of the path queue asks L2 for its lines: the rays of a chunk are
+// handed out a few at a time as lanes finish, and each hand-out would otherwise wait for HBM with the whole
+// warp standing still.  Eight arrays (origin, direction, weight, pixel), sixteen entries per line.
+#ifndef ERT_WF_PREFETCH_CHUNK
+#define ERT_WF_PREFETCH_CHUNK 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_path_chunk(const WfBuf &wf, unsigned long long begin, unsigned long long end, int lane)
+{
+#if ERT_WF_PREFETCH_CHUNK
+    const size_t np = (size_t)wf.n_pad;
+    const int arr = lane & 7;
+    for (unsigned long long e = begin + (unsigned long long)((lane >> 3) * 16); e < end; e += 64) {
+        const void *p = arr < 6 ? (const void *)(wf.q_ray + (size_t)arr * np + e)
+                                : (arr == 6 ? (const void *)(wf.q_w + e) : (const void *)(wf.q_pid + e));
+        prefetch_l2(p);
+    }
+#endif
+}
+
 // Path rays of one bounce: nearest_object_intersecting_ray/2 (erl:300-346) for every ray of
 // the path queue (FIRST: for every pixel, rays generated on the fly).  EMIT: the batch also turns
 // its hits into hit records (what wf_emit_hits does from the result arrays) — the warp is back
@@ -1213,6 +1251,7 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
         if (32 - __popc(idle) < kRefillBelow && !drained) {
             if (pos >= end) {
                 if (!next_chunk(cursor, n, lane, pos, end)) { drained = true; pos = end = 0; }
+                else prefetch_path_chunk(wf, pos, end, lane);
             }
             if (pos < end) {
                 const unsigned long long i64 = pos + (unsigned long long)rank_in(idle, lane);

@@ -297,15 +297,15 @@ def test_walk_is_complete_awkward_scenes(cg, case):
 
 @pytest.mark.parametrize("density", [0.2, 0.35, 2.0])
 def test_packed_blocks_hold_the_same_lists(cg, density):
-    """The device walks 128-byte blocks (6 spheres inside, longer lists in overflow groups of four): every cell's
-    block and overflow range must decode to exactly the list the completeness tests above check."""
+    """The device walks two 128-byte blocks per cell (6 spheres in each, longer lists in overflow groups of four):
+    every cell's blocks and overflow range must decode to exactly the list the completeness tests above check."""
     rng = np.random.default_rng(11)
     c, r = rand_scene(rng, 4000, (40, 16, 40), 0.2, 1.2)
     g = Grid(cg, c, r, density=density)
     assert g.enabled
     L = cg
     n_cells, n_over, n_refs = len(g.cells), L.cg_n_over(g.h), L.cg_n_refs(g.h)
-    blocks = np.ctypeslib.as_array(ctypes.cast(L.cg_blocks(g.h), ctypes.POINTER(ctypes.c_uint32)), (n_cells, 32)).copy()
+    blocks = np.ctypeslib.as_array(ctypes.cast(L.cg_blocks(g.h), ctypes.POINTER(ctypes.c_uint32)), (n_cells, 2, 32)).copy()
     over_sph = np.ctypeslib.as_array(ctypes.cast(L.cg_over_sph(g.h), ctypes.POINTER(ctypes.c_int32)), (n_over,)).copy()
     over_f = np.ctypeslib.as_array(ctypes.cast(L.cg_over_filter(g.h), ctypes.POINTER(ctypes.c_float)), (n_over, 4)).copy()
     ref_f = np.ctypeslib.as_array(ctypes.cast(L.cg_ref_filter(g.h), ctypes.POINTER(ctypes.c_float)), (n_refs, 4)).copy()
@@ -315,25 +315,25 @@ def test_packed_blocks_hold_the_same_lists(cg, density):
         word = int(g.cells[cell])
         first, cnt = word >> 7, word & 127
         b = blocks[cell]
-        f_in = b[:24].view(np.float32).reshape(6, 4)
-        s_in = b[24:30].view(np.int32)
-        assert int(b[30]) == cnt
-        more = int(b[31])
-        n_in = min(cnt, 6)
+        f_in = np.concatenate([b[0, :24].view(np.float32).reshape(6, 4), b[1, :24].view(np.float32).reshape(6, 4)])
+        s_in = np.concatenate([b[0, 24:30].view(np.int32), b[1, 24:30].view(np.int32)])
+        assert int(b[0, 30]) == cnt
+        more = int(b[0, 31])
+        n_in = min(cnt, 12)
         assert np.array_equal(s_in[:n_in], g.ref_sph[first:first + n_in])
         assert np.array_equal(f_in[:n_in], ref_f[first:first + n_in])
         assert np.all(s_in[n_in:] == -1) and np.all(f_in[n_in:, 3] < -1e38)          # padding never passes
-        if cnt > 6:
-            n_ov = cnt - 6
+        if cnt > 12:
+            n_ov = cnt - 12
             assert more % 4 == 0 and more + (n_ov + 3) // 4 * 4 + 4 <= n_over          # one group past the list exists
-            assert np.array_equal(over_sph[more:more + n_ov], g.ref_sph[first + 6:first + cnt])
-            assert np.array_equal(over_f[more:more + n_ov], ref_f[first + 6:first + cnt])
+            assert np.array_equal(over_sph[more:more + n_ov], g.ref_sph[first + 12:first + cnt])
+            assert np.array_equal(over_f[more:more + n_ov], ref_f[first + 12:first + cnt])
             pad = (n_ov + 3) // 4 * 4
             assert np.all(over_sph[more + n_ov:more + pad] == -1) and np.all(over_f[more + n_ov:more + pad, 3] < -1e38)
         longest = max(longest, cnt)
     assert np.all(over_sph[-4:] == -1)
-    if density <= 0.35:
-        assert longest > 6                                           # the overflow path is exercised
+    if density <= 0.2:
+        assert longest > 12                                          # the overflow path is exercised
     g.close()
 
 
