@@ -182,6 +182,10 @@ __device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef ERT_GRID_PREFETCH
+#define ERT_GRID_PREFETCH 3            /* 0: both blocks of the next cell to L1, 1: L1 + L2, 2: both to L2, 3: first block to L1 only — all within 0.4 % on C4 */
+#endif
 __device__ __forceinline__ void ldg256(const void *p, float (&v)[8])
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -558,8 +562,18 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         TALLY(cell);
         te = grid_advance(g, r, cg);
         if (g.id >= 0 && !(te > g.cullk)) {
+#if ERT_GRID_PREFETCH == 0
             prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
             prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4 + 8);
+#elif ERT_GRID_PREFETCH == 1
+            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
+            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4 + 8);
+#elif ERT_GRID_PREFETCH == 2
+            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4);
+            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4 + 8);
+#else
+            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
+#endif
         }
         if (hd.x) break;
         if (te > g.cullk) { g.id = -1; return false; }
@@ -1040,7 +1054,6 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 #ifndef ERT_WF_PREFETCH_CHUNK
 #define ERT_WF_PREFETCH_CHUNK 1
 #endif
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_path_chunk(const WfBuf &wf, unsigned long long begin, unsigned long long end, int lane)
 {
 #if ERT_WF_PREFETCH_CHUNK
