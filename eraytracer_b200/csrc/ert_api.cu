@@ -741,7 +741,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     const bool no_sort = unsorted || (!shadows_walk && !force_sort);
     // every light has a direction grid and the hits stay in arrival order: shadow rays and the light fold in one kernel
     static const bool env_no_fuse = getenv("ERT_WF_NO_FUSE") != nullptr;
-    const bool fused_shade = !env_no_fuse && !scan && !shadows_walk && no_sort && d.n_lights <= 32;
+    const bool fused_shade = !env_no_fuse && !scan && !shadows_walk && no_sort && d.n_lights <= kSsMaxLights;
 #define WF_CHECK(what)                                                                 \
     do {                                                                               \
         if (debug_sync) {                                                              \
@@ -908,6 +908,8 @@ int finish_slot(ert_scene *s, Slot &sl)
 #ifdef ERT_PROBE
     fprintf(stderr, "PROBE path rays %llu filter %llu exact %llu cell %llu :", c0[CNT_RAYS], c0[CNT_FILTER], c0[CNT_EXACT_SPH], c0[CNT_CELL]);
     for (int k = 0; k < 8; k++) fprintf(stderr, " p%d=%llu", k, c0[CNT_PROBE + k]);
+    fprintf(stderr, "\nPROBE shadow rays %llu filter %llu exact %llu :", c1[CNT_RAYS], c1[CNT_FILTER], c1[CNT_EXACT_SPH]);
+    for (int k = 0; k < 8; k++) fprintf(stderr, " p%d=%llu", k, c1[CNT_PROBE + k]);
     fprintf(stderr, "\n");
 #endif
     sl.stats.bounces_recorded = sl.wf_levels;

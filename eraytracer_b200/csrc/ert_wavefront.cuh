@@ -1605,19 +1605,121 @@ wf_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParam
     }
 }
 
+// ------------------------------------------------------------------ shadow rays: FP32 triage
+// Most shadow rays of a crowded scene are blocked, and nearly always by the nearest sphere of their direction
+// cell.  shadow_blocked() proves that in FP32 where it can: the light's ray towards the hit certainly meets the
+// cell's first candidate S (impact parameter by cross product, so the error grows with the distance from the
+// light, not with its square), S's reference Distance certainly lies below the target's, and therefore
+// "nearest == Object" (erl:263) is false whatever else the scan finds — no FP64 normalise, no literal tests.
+// It answers true only with every rounding of its own arithmetic AND of the reference's FP64 evaluation inside
+// the margins below; everything else (lit rays, near ties, grazing rays, awkward geometry) is left to the
+// literal path.
+//
+// Frame: the light O is the origin.  With u = 2^-24, rho = |C - O|, L = |P - O|:
+//   direction  df = fl(P - O) normalised in FP32 (products, sums, rsqrtf <= 2 ulp): |df - D^| <= 7.4u  (12u used)
+//   centre     cf - fl(O): |error| <= eta_c + sqrt(3) u |O|_inf + u rho =: ec
+//   impact     q = (C - O) x D^;  |qf - q| <= ec + 17u rho                      (24u rho used)
+//   along      b = (C - O) . D^;  |bf - b| <= ec + 12.6u rho                    (24u rho used)
+//   radius     R = fl_up(r^2 (1 + 2^-18) + pad_c), so r^2 >= (R - pad_c_max)(1 - 2^-17) - 8uR
+// Reference (erl:364-397, A = D.D = 1 +- 1e-15): Discriminant = 4A(r^2 - q^2) >= 0.001, T = b - sqrt(r^2 - q^2),
+// both roots >= 0 iff the origin is outside and b > 0; its FP64 evaluation moves Discriminant by <= 5e-15 rho^2 and
+// T by <= 6e-14 rho^2 once Discriminant >= 0.0016: the 1e-12 rho^2 terms cover both.
+__device__ __forceinline__ unsigned int light_cell_of(float dx, float dy, float dz, int res)
+{
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    int m = 0;
+    float am = ax, dm = dx, du = dy, dv = dz;
+    if (ay > am) { m = 1; am = ay; dm = dy; du = dz; dv = dx; }
+    if (az > am) { m = 2; am = az; dm = dz; du = dx; dv = dy; }
+    const int face = 2 * m + (dm < 0.0f ? 1 : 0);
+    const float inv = __frcp_rn(am);
+    const float u = du * inv, v = dv * inv;
+    const float half = 0.5f * (float)res;
+    int iu = (int)floorf((u + 1.0f) * half), iv = (int)floorf((v + 1.0f) * half);
+    iu = min(max(iu, 0), res - 1);
+    iv = min(max(iv, 0), res - 1);
+    return (unsigned int)((face * res + iv) * res + iu);
+}
+__device__ __forceinline__ bool shadow_blocked(const DevScene &sc, const LightGridDev &lg, const double *lt, d3 P,
+                                               int target, float4 tf)
+{
+    const float u = ERT_U;
+    const float fx = (float)(P.x - lt[3]), fy = (float)(P.y - lt[4]), fz = (float)(P.z - lt[5]);
+    const float l2 = fx * fx + fy * fy + fz * fz;
+    if (!(l2 > 1e-20f && l2 < 1e20f)) return false;
+    const float inv = rsqrtf(l2);
+    const float dx = fx * inv, dy = fy * inv, dz = fz * inv;
+    float c[8];
+    ldg256(lg.head + light_cell_of(dx, dy, dz, lg.res), c);
+    const int sph = __float_as_int(c[4]);
+    if (sph < 0 || obj_code(OBJ_SPHERE, sph) == target) return false;
+    const float ox = (float)lt[3], oy = (float)lt[4], oz = (float)lt[5];
+    const float ec0 = 1.01f * (sc.eta_c_max + 1.75f * u * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)));
+    // the candidate
+    const float cx = c[0] - ox, cy = c[1] - oy, cz = c[2] - oz;
+    const float rho2 = cx * cx + cy * cy + cz * cz;
+    const float rho = sqrtf(rho2);
+    const float b = dx * cx + dy * cy + dz * cz;
+    const float qx = cy * dz - cz * dy, qy = cz * dx - cx * dz, qz = cx * dy - cy * dx;
+    const float err = ec0 + 26.f * u * rho;                          // bounds both |qf - q| and |bf - b|
+    const float qmax = sqrtf(qx * qx + qy * qy + qz * qz) * (1.f + 8.f * u) + err;
+    const float R = c[3];
+    const float fp64_noise = 1e-12f * rho2;
+    // lower bound of r^2 - q^2, its own roundings taken off
+    const float T = ((R - sc.pad_c_max) * (1.f - 7.62939453125e-6f) - 8.f * u * R) - qmax * qmax * (1.f + 4.f * u) - 8.f * u * R;
+    if (!(T > 0.0004f + fp64_noise)) return false;                   // Discriminant >= 0.001 with room to spare
+    if (!(b - err > sqrtf(R) * (1.f + 4.f * u))) return false;       // the light is outside S and S lies ahead
+    float s_up = b + err - sqrtf(T) * (1.f - 4.f * u);               // >= the reference's Distance of S ...
+    s_up += 4.f * u * b + 4e-6f * fabsf(s_up) + fp64_noise + 1e-7f;  // ... and its evaluation
+    // lower bound of the target's Distance, should the ray meet the target at all
+    float s_lo;
+    if (obj_type(target) == OBJ_SPHERE) {
+        const float tx = tf.x - ox, ty = tf.y - oy, tz = tf.z - oz;
+        const float trho2 = tx * tx + ty * ty + tz * tz;
+        const float tb = dx * tx + dy * ty + dz * tz;
+        s_lo = tb - (ec0 + 26.f * u * sqrtf(trho2)) - sqrtf(tf.w) * (1.f + 4.f * u) - 4.f * u * fabsf(tb) - 1e-12f * trho2 - 1e-7f;
+    } else if (obj_type(target) == OBJ_PLANE) {
+        // the ray meets the plane where the hit lies (to the rounding of the hit location) unless it grazes it
+        const double *pl = sc.planes + 4 * obj_index(target);
+        const float nx = (float)pl[0], ny = (float)pl[1], nz = (float)pl[2];
+        const float nd = nx * dx + ny * dy + nz * dz;
+        if (!(fabsf(nd) > 1e-3f * sqrtf(nx * nx + ny * ny + nz * nz))) return false;
+        s_lo = l2 * inv * (1.f - 1e-5f) - 1e-7f;
+    } else {
+        return false;
+    }
+    return s_up < s_lo;
+}
+
 // shadow_factor/4 and the light fold in ONE pass over the hits, for scenes whose lights all have a direction grid
-// (no walk, no per-warp occluder ring).  A lane keeps one hit and asks its lights one after the other, so the warp
-// still works in one direction grid at a time; the hit location and the target's sphere are fetched once instead
-// of once per light, the shadow factors never travel through HBM, and the colour update follows at once
-// (erl:209-252 in forward form, exactly wf_shade's arithmetic).
+// (no walk, no per-warp occluder ring).  A warp takes a chunk of up to 128 hits and goes through it in three
+// phases, each of which packs its work over the lanes first:
+//   1. triage: every (hit, light) pair goes through shadow_blocked(); the pairs it cannot settle are listed in
+//      shared memory;
+//   2. the listed pairs, 32 at a time and one per lane whatever hit they belong to, take the literal path
+//      (FP64 direction, the target's literal test — "nearest == Object" needs the target hit —, planes and
+//      triangles, the candidates of the direction cell) and mark the lights that reach their hit;
+//   3. the hits some light reaches, again 32 at a time, fold those lights into their pixel in list order
+//      (erl:209-252 in forward form, wf_shade's arithmetic).
+// The shadow factors never travel through HBM, and the FP64 work runs on nearly full warps although only a
+// third of the rays and a third of the hits need it.
 #ifndef ERT_SS_MINBLOCKS
 #define ERT_SS_MINBLOCKS 4
 #endif
+#ifndef ERT_SS_TRIAGE
+#define ERT_SS_TRIAGE 1
+#endif
+constexpr int kSsMaxLights = 8;                  // three bits of a pair's entry; ert_api.cu uses the kernel for <= 8 lights
+static_assert(kWfChunk <= 128, "a chunk's hits are numbered with seven bits");
 template <bool COUNT>
 __global__ void __launch_bounds__(kWfThreads, ERT_SS_MINBLOCKS)
 wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ FrameParams fp,
                 const __grid_constant__ WfBuf wf, int bounce)
 {
+    __shared__ unsigned int sh_lit_all[kWfThreads / 32][kWfChunk];                      // lights that reach each hit
+    __shared__ unsigned short sh_list_all[kWfThreads / 32][kWfChunk * kSsMaxLights];   // open pairs: slot << 3 | light; then lit slots
+    unsigned int *sh_lit = sh_lit_all[threadIdx.x >> 5];
+    unsigned short *sh_list = sh_list_all[threadIdx.x >> 5];
     unsigned int *ctr = wf.ctr + bounce * kWfCtr;
     const unsigned int n_hits = ctr[WF_NHITS];
     unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ctr + WF_FETCH_SHADOW);
@@ -1627,47 +1729,104 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
     Tally<COUNT> tl;
     unsigned int rays = 0;
     unsigned long long begin, end;
+    // appends `mine` entries of this lane to the list (every lane calls); returns where this lane's entries start
+    auto reserve = [&](int mine, int &n_list) -> int {
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int at = n_list + incl - mine;
+        n_list += __shfl_sync(0xffffffffu, incl, 31);
+        return at;
+    };
     while (next_chunk(cursor, (unsigned long long)n_hits, lane, begin, end)) {
-        for (unsigned long long b0 = begin; b0 < end; b0 += 32) {
-            const unsigned long long j = b0 + lane;
-            const bool valid = j < end;
-            const unsigned int h = valid ? (unsigned int)j : (unsigned int)(end - 1);
-            const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
-            const d3 P = mk(r0.x, r0.y, r0.z);
-            const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
-            const int order = (int)(__double_as_longlong(r0.w) >> 32);
-            // on their way to L1 while the first direction is normalised
-            if (obj_type(target) == OBJ_SPHERE) prefetch_l1(sc.sph_exact + obj_index(target));
-            unsigned int litmask = 0u;
-            for (int l = 0; l < L; l++) {
-                __syncwarp();
-                if (!valid) continue;
-                rays++;
+        const int nb = (int)(end - begin);
+        // ---- 1. triage
+        int n_list = 0;
+        for (int s0 = 0; s0 < nb; s0 += 32) {
+            const int slot = s0 + lane;
+            unsigned int open = 0u;                                  // lights whose ray the triage could not settle
+            if (slot < nb) {
+                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
+                rays += (unsigned int)L;
+                sh_lit[slot] = 0u;
+#if ERT_SS_TRIAGE
+                const d3 P = mk(r0.x, r0.y, r0.z);
+                const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
+                float4 tf = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (obj_type(target) == OBJ_SPHERE) tf = __ldg(sc.sph_filter + obj_index(target));
+                for (int l = 0; l < L; l++) {
+                    if (!shadow_blocked(sc, sc.lgrids[l], sc.lights + 9 * (size_t)l, P, target, tf)) open |= 1u << l;
+                }
+#else
+                open = (1u << L) - 1u;
+#endif
+            }
+            int at = reserve(__popc(open), n_list);
+            while (open) {
+                const int l = __ffs((int)open) - 1;
+                open &= open - 1u;
+                sh_list[at++] = (unsigned short)((slot << 3) | l);
+            }
+        }
+        PROBE(0, lane == 0 ? (unsigned int)n_list : 0u);
+        __syncwarp();
+        // ---- 2. the literal path for the open pairs
+        for (int k0 = 0; k0 < n_list; k0 += 32) {
+            const int k = k0 + lane;
+            if (k < n_list) {
+                const unsigned int pr = sh_list[k];
+                const int slot = (int)(pr >> 3), l = (int)(pr & 7u);
+                const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
+                const d3 Ph = mk(q0.x, q0.y, q0.z);
+                const int tgt = (int)(__double_as_longlong(q0.w) & 0xffffffffll);
+                const int order = (int)(__double_as_longlong(q0.w) >> 32);
                 const double *lt = sc.lights + 9 * (size_t)l;
                 const d3 O = mk(lt[3], lt[4], lt[5]);
-                const d3 D = vnormalize(vsub(P, O));                   // erl:257-260
+                const d3 D = vnormalize(vsub(Ph, O));                  // erl:257-260
                 const double a = D.x * D.x + D.y * D.y + D.z * D.z;
                 double t;
                 // "nearest == Object" (erl:263) <=> Object is hit and nothing beats its (t, order)
-                if (!object_exact(sc, target, O, D, a, t)) continue;
-                Hit best;
-                best.t = t; best.order = order; best.obj = target;
-                scan_others_shadow<COUNT>(sc, O, D, best, target, tl);
-                bool lit = best.obj == target;
-                if (lit && sc.n_spheres > 0) {
-                    SRay f;
-                    double a2, inv;
-                    make_sray(sc, O, D, f, a2, inv);
-                    lit = !light_grid_occluded<COUNT>(sc, sc.lgrids[l], f, O, D, a, inv, best, target, tl);
+                if (object_exact(sc, tgt, O, D, a, t)) {
+                    Hit best;
+                    best.t = t; best.order = order; best.obj = tgt;
+                    scan_others_shadow<COUNT>(sc, O, D, best, tgt, tl);
+                    bool lit = best.obj == tgt;
+                    if (lit && sc.n_spheres > 0) {
+                        SRay f;
+                        double a2, inv;
+                        make_sray(sc, O, D, f, a2, inv);
+                        lit = !light_grid_occluded<COUNT>(sc, sc.lgrids[l], f, O, D, a, inv, best, tgt, tl);
+                    }
+                    if (lit) atomicOr(sh_lit + slot, 1u << l);
+                    PROBE(2, lit ? 1u : 0u);
                 }
-                if (lit) litmask |= 1u << l;
             }
-            __syncwarp();
-            // A hit no light reaches adds S * W = (0,0,0) * W to its pixel: the colour buffer starts at +0.0 and a sum
-            // that starts there is never -0.0, so for any finite W the addition changes no bit and the record's tail
-            // stays unread.  (A non-finite W needs a reflectivity beyond 1e60: BEAM floats cannot hold the products
-            // the reference would form with it, erl:239-247 raises badarith long before.)
-            if (valid && litmask) {
+        }
+        __syncwarp();
+        // ---- 3. the fold.  A hit no light reaches adds S * W = (0,0,0) * W to its pixel: the colour buffer starts at
+        // +0.0 and a sum that starts there is never -0.0, so for any finite W the addition changes no bit and the
+        // record's tail stays unread.  (A non-finite W needs a reflectivity beyond 1e60: BEAM floats cannot hold the
+        // products the reference would form with it, erl:239-247 raises badarith long before.)
+        n_list = 0;
+        for (int s0 = 0; s0 < nb; s0 += 32) {
+            const int slot = s0 + lane;
+            const bool any = slot < nb && sh_lit[slot] != 0u;
+            const int at = reserve(any ? 1 : 0, n_list);
+            if (any) sh_list[at] = (unsigned short)slot;
+        }
+        __syncwarp();
+        for (int k0 = 0; k0 < n_list; k0 += 32) {
+            const int k = k0 + lane;
+            if (k < n_list) {
+                const int slot = (int)sh_list[k];
+                const unsigned int litmask = sh_lit[slot];
+                const size_t h = (size_t)begin + slot;
+                const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+                const d3 P = mk(q0.x, q0.y, q0.z);
+                const int target = (int)(__double_as_longlong(q0.w) & 0xffffffffll);
                 HitTail ht;
                 {
                     const uint4 *st = reinterpret_cast<const uint4 *>(wf.hit_tail + h);
@@ -1688,6 +1847,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 wf.C[pid] = Cnew.x; wf.C[np + pid] = Cnew.y; wf.C[2 * np + pid] = Cnew.z;
             }
         }
+        __syncwarp();
     }
     flush_counters<COUNT>(fp, (int)rays, tl);
 }
