@@ -908,6 +908,13 @@ int finish_slot(ert_scene *s, Slot &sl)
 #ifdef ERT_PROBE
     fprintf(stderr, "PROBE path rays %llu filter %llu exact %llu cell %llu :", c0[CNT_RAYS], c0[CNT_FILTER], c0[CNT_EXACT_SPH], c0[CNT_CELL]);
     for (int k = 0; k < 8; k++) fprintf(stderr, " p%d=%llu", k, c0[CNT_PROBE + k]);
+    {
+        unsigned long long r[8];
+        cudaMemcpyFromSymbol(r, g_sb_reason, sizeof r);
+        fprintf(stderr, "\nPROBE triage open reasons: empty %llu rest-beyond-target %llu list-exhausted %llu tries-exhausted %llu (%llu)", r[0], r[1], r[2], r[3], r[4]);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_sb_reason, z, sizeof z);
+    }
     fprintf(stderr, "\nPROBE shadow rays %llu filter %llu exact %llu :", c1[CNT_RAYS], c1[CNT_FILTER], c1[CNT_EXACT_SPH]);
     for (int k = 0; k < 8; k++) fprintf(stderr, " p%d=%llu", k, c1[CNT_PROBE + k]);
     fprintf(stderr, "\n");

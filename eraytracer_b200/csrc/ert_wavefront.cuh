@@ -1640,6 +1640,16 @@ __device__ __forceinline__ unsigned int light_cell_of(float dx, float dy, float 
     iv = min(max(iv, 0), res - 1);
     return (unsigned int)((face * res + iv) * res + iu);
 }
+#ifndef ERT_TRIAGE_CANDS
+#define ERT_TRIAGE_CANDS 4
+#endif
+constexpr int kTriageCands = ERT_TRIAGE_CANDS;   // candidates of a direction cell the triage looks at
+#ifdef ERT_PROBE
+__device__ unsigned long long g_sb_reason[8];
+#define SB_REASON(k) atomicAdd(&g_sb_reason[k], 1ull)
+#else
+#define SB_REASON(k) do { } while (0)
+#endif
 __device__ __forceinline__ bool shadow_blocked(const DevScene &sc, const LightGridDev &lg, const double *lt, d3 P,
                                                int target, float4 tf)
 {
@@ -1651,26 +1661,9 @@ __device__ __forceinline__ bool shadow_blocked(const DevScene &sc, const LightGr
     const float dx = fx * inv, dy = fy * inv, dz = fz * inv;
     float c[8];
     ldg256(lg.head + light_cell_of(dx, dy, dz, lg.res), c);
-    const int sph = __float_as_int(c[4]);
-    if (sph < 0 || obj_code(OBJ_SPHERE, sph) == target) return false;
+    if (__float_as_int(c[4]) < 0) { SB_REASON(0); return false; }   // nothing listed in this direction
     const float ox = (float)lt[3], oy = (float)lt[4], oz = (float)lt[5];
     const float ec0 = 1.01f * (sc.eta_c_max + 1.75f * u * fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)));
-    // the candidate
-    const float cx = c[0] - ox, cy = c[1] - oy, cz = c[2] - oz;
-    const float rho2 = cx * cx + cy * cy + cz * cz;
-    const float rho = sqrtf(rho2);
-    const float b = dx * cx + dy * cy + dz * cz;
-    const float qx = cy * dz - cz * dy, qy = cz * dx - cx * dz, qz = cx * dy - cy * dx;
-    const float err = ec0 + 26.f * u * rho;                          // bounds both |qf - q| and |bf - b|
-    const float qmax = sqrtf(qx * qx + qy * qy + qz * qz) * (1.f + 8.f * u) + err;
-    const float R = c[3];
-    const float fp64_noise = 1e-12f * rho2;
-    // lower bound of r^2 - q^2, its own roundings taken off
-    const float T = ((R - sc.pad_c_max) * (1.f - 7.62939453125e-6f) - 8.f * u * R) - qmax * qmax * (1.f + 4.f * u) - 8.f * u * R;
-    if (!(T > 0.0004f + fp64_noise)) return false;                   // Discriminant >= 0.001 with room to spare
-    if (!(b - err > sqrtf(R) * (1.f + 4.f * u))) return false;       // the light is outside S and S lies ahead
-    float s_up = b + err - sqrtf(T) * (1.f - 4.f * u);               // >= the reference's Distance of S ...
-    s_up += 4.f * u * b + 4e-6f * fabsf(s_up) + fp64_noise + 1e-7f;  // ... and its evaluation
     // lower bound of the target's Distance, should the ray meet the target at all
     float s_lo;
     if (obj_type(target) == OBJ_SPHERE) {
@@ -1688,7 +1681,38 @@ __device__ __forceinline__ bool shadow_blocked(const DevScene &sc, const LightGr
     } else {
         return false;
     }
-    return s_up < s_lo;
+    // the candidates of the cell, nearest first, until one certainly blocks the ray or the rest lie beyond the target
+    unsigned int e = __float_as_uint(c[6]);
+    const unsigned int e1 = __float_as_uint(c[7]);
+#pragma unroll 1
+    for (int tries = 0; tries < kTriageCands; tries++) {
+        if (c[5] > s_lo) { SB_REASON(1); return false; }             // dmin: this and all later ones are too far
+        const float cx = c[0] - ox, cy = c[1] - oy, cz = c[2] - oz, R = c[3];
+        const int sph = __float_as_int(c[4]);
+        const bool more = e < e1;
+        if (more) ldg256(lg.cand + e, c);                            // in flight while this candidate is tested
+        e++;
+        if (obj_code(OBJ_SPHERE, sph) != target) {
+            const float rho2 = cx * cx + cy * cy + cz * cz;
+            const float rho = sqrtf(rho2);
+            const float b = dx * cx + dy * cy + dz * cz;
+            const float qx = cy * dz - cz * dy, qy = cz * dx - cx * dz, qz = cx * dy - cy * dx;
+            const float err = ec0 + 26.f * u * rho;                  // bounds both |qf - q| and |bf - b|
+            const float qmax = sqrtf(qx * qx + qy * qy + qz * qz) * (1.f + 8.f * u) + err;
+            const float fp64_noise = 1e-12f * rho2;
+            // lower bound of r^2 - q^2, its own roundings taken off
+            const float T = ((R - sc.pad_c_max) * (1.f - 7.62939453125e-6f) - 8.f * u * R) - qmax * qmax * (1.f + 4.f * u) - 8.f * u * R;
+            // Discriminant >= 0.001 with room to spare; the light is outside S and S lies ahead
+            if (T > 0.0004f + fp64_noise && b - err > sqrtf(R) * (1.f + 4.f * u)) {
+                float s_up = b + err - sqrtf(T) * (1.f - 4.f * u);               // >= the reference's Distance of S ...
+                s_up += 4.f * u * b + 4e-6f * fabsf(s_up) + fp64_noise + 1e-7f;  // ... and its evaluation
+                if (s_up < s_lo) return true;
+            }
+        }
+        if (!more) { SB_REASON(2); return false; }
+    }
+    SB_REASON(3);
+    return false;
 }
 
 // shadow_factor/4 and the light fold in ONE pass over the hits, for scenes whose lights all have a direction grid
