@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ERT_B200_LIB") or os.path.join(HERE, "lib", "libert_b
 
 ERT_OK, ERT_ERR_BADARG, ERT_ERR_NO_DEVICE, ERT_ERR_CUDA, ERT_ERR_NOMEM = 0, 1, 2, 3, 4
 FMT_RGB8, FMT_F32, FMT_F64 = 0, 1, 2
-ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL, ACCEL_GRID = 0, 1, 2, 3, 4, 5
+ACCEL_AUTO, ACCEL_EXACT, ACCEL_LINEAR, ACCEL_BVH, ACCEL_BVH_MEGAKERNEL, ACCEL_GRID, ACCEL_WARP = 0, 1, 2, 3, 4, 5, 6
 FLAG_COUNT_TESTS = 1
 FLAG_WF_UNSORTED = 2
 FLAG_NO_LIGHT_GRID = 4
@@ -24,7 +24,7 @@ MAX_SLOTS = 4
 FORMATS = {"rgb8": FMT_RGB8, "f32": FMT_F32, "f64": FMT_F64}
 FORMAT_DTYPES = {FMT_RGB8: np.uint8, FMT_F32: np.float32, FMT_F64: np.float64}
 ACCELS = {"auto": ACCEL_AUTO, "exact": ACCEL_EXACT, "linear": ACCEL_LINEAR, "bvh": ACCEL_BVH,
-          "bvh_mega": ACCEL_BVH_MEGAKERNEL, "grid": ACCEL_GRID}
+          "bvh_mega": ACCEL_BVH_MEGAKERNEL, "grid": ACCEL_GRID, "warp": ACCEL_WARP}
 ACCEL_NAMES = {v: k for k, v in ACCELS.items()}
 
 

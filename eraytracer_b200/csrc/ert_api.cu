@@ -1184,7 +1184,7 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
 {
     if (!scene || (n_rays > 0 && (!rays6 || !order_out || !t_out))) return fail(ERT_ERR_BADARG, "NULL argument");
     if (n_rays < 0) return fail(ERT_ERR_BADARG, "negative ray count");
-    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_GRID) return fail(ERT_ERR_BADARG, "unknown accel");
+    if (accel < ERT_ACCEL_AUTO || accel > ERT_ACCEL_WARP) return fail(ERT_ERR_BADARG, "unknown accel");
     if (n_rays == 0) return ERT_OK;
     std::lock_guard<std::mutex> lock(scene->mu);
     CU(cudaSetDevice(scene->device));
@@ -1207,7 +1207,13 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
     TRY(cudaMemcpyAsync(d_rays, rays6, (size_t)n_rays * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     {
         unsigned blocks = (unsigned)((n_rays + 255) / 256);
+        Slot &sl0 = scene->slots[0];                 // the kernel's device time is left in slot 0's stats.kernel_ms
+        TRY(cudaEventRecord(sl0.ev0, st));
         switch (accel) {
+        case ERT_ACCEL_WARP:
+            if (n_rays > (1ll << 26)) { rc = fail(ERT_ERR_BADARG, "ERT_ACCEL_WARP takes at most 2^26 rays per call"); goto done; }
+            trace_rays_warp_kernel<<<(unsigned)((n_rays * 32 + 255) / 256), 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t);
+            break;
         case ERT_ACCEL_EXACT: trace_rays_kernel<1><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         case ERT_ACCEL_LINEAR: trace_rays_kernel<2><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
         case ERT_ACCEL_BVH_MEGAKERNEL: trace_rays_kernel<3><<<blocks, 256, 0, st>>>(scene->dev, n_rays, d_rays, d_ord, d_t); break;
@@ -1216,9 +1222,14 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
         }
     }
     TRY(cudaGetLastError());
+    TRY(cudaEventRecord(scene->slots[0].ev1, st));
     TRY(cudaMemcpyAsync(order_out, d_ord, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(t_out, d_t, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, scene->slots[0].ev0, scene->slots[0].ev1) == cudaSuccess) scene->slots[0].stats.kernel_ms = ms;
+    }
 #undef TRY
 done:
     if (d_rays) cudaFree(d_rays);

@@ -970,6 +970,55 @@ trace_rays_kernel(const __grid_constant__ DevScene sc, long long n_rays, const d
     t_out[i] = q.best.obj < 0 ? 0.0 : q.best.t;
 }
 
+// ---- ray batch, one warp per ray (ERT_ACCEL_WARP): warp-wide nearest-hit reduction ----
+// The scan of erl:300-346 split over the 32 lanes of a warp: lane k takes spheres k, k+32, ... through the FP32 filter
+// and the literal test, planes and triangles go to lane 0, and the nearest object is the lexicographic minimum of
+// (Distance, list position) over the lanes' results — erl:319's strict '>' over the list order — found with three
+// __reduce_min_sync steps on the order-preserving integer image of the double.
+__device__ __forceinline__ unsigned long long sortable_bits(double t)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(t);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void __launch_bounds__(256)
+trace_rays_warp_kernel(const __grid_constant__ DevScene sc, long long n_rays, const double *__restrict__ rays6,
+                       int *__restrict__ order_out, double *__restrict__ t_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_rays) return;                                   // the whole warp leaves together
+    const d3 O = mk(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
+    const d3 D = mk(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
+    Tally<false> tl;
+    Hit best;
+    best.obj = -1; best.t = 0.0; best.order = 0x7fffffff;
+    if (lane == 0) scan_others<false>(sc, O, D, best, -1, tl);
+    // every lane starts from lane 0's plane / triangle incumbent: it culls, and it is a candidate of the minimum
+    best.t = __shfl_sync(0xffffffffu, best.t, 0);
+    best.order = __shfl_sync(0xffffffffu, best.order, 0);
+    best.obj = __shfl_sync(0xffffffffu, best.obj, 0);
+    FRay f;
+    make_fray(sc, O, D, f, false);
+    float cull = cull_from(f, best);
+    for (int s = lane; s < sc.n_spheres; s += 32)
+        try_sphere<false>(sc, f, O, D, __ldg(sc.sph_filter + s), s, -1, best, cull, tl);
+    // lexicographic minimum of (Distance, list position) over the lanes
+    const bool have = best.obj >= 0;
+    const unsigned long long key = have ? sortable_bits(best.t) : ~0ull;
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int min_hi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int min_lo = __reduce_min_sync(0xffffffffu, hi == min_hi ? lo : 0xffffffffu);
+    const bool tied = have && hi == min_hi && lo == min_lo;
+    const unsigned int min_ord = __reduce_min_sync(0xffffffffu, tied ? (unsigned int)best.order ^ 0x80000000u : 0xffffffffu);
+    const unsigned int winners = __ballot_sync(0xffffffffu, tied && ((unsigned int)best.order ^ 0x80000000u) == min_ord);
+    if (winners == 0u) {
+        if (lane == 0) { order_out[i] = -1; t_out[i] = 0.0; }
+    } else if (lane == __ffs((int)winners) - 1) {
+        order_out[i] = best.order;
+        t_out[i] = best.t;
+    }
+}
+
 // ---- FP32 issue-peak probe: register-resident FFMA chains --------------------------------
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float seed)
 {

@@ -123,6 +123,11 @@ typedef struct ert_scene_desc {
                                * over the spheres (3-D DDA, FP32 conservative) instead of walking the BVH.  Built
                                * for scenes of many small spheres; scenes without one (and rays that start far
                                * outside the scene) use the BVH.  ERT_ACCEL_AUTO prefers it when the scene has one. */
+#define ERT_ACCEL_WARP    6   /* ert_trace_rays only: one WARP per ray — the lanes stride over the sphere list (FP32 filter,
+                               * FP64 literal test on their survivors) and the nearest hit is the warp-wide lexicographic
+                               * minimum of (Distance, list position), three __reduce_min_sync steps.  The optional
+                               * warp-wide reduction of the design brief; measured against the thread-per-ray scan in
+                               * DESIGN.md (it loses wherever the rays of a warp can share the sphere loop). */
 
 #define ERT_FLAG_COUNT_TESTS  1u  /* instrumented run: fill the test counters in ert_stats (slower) */
 #define ERT_FLAG_TIME_KERNELS  8u  /* ERT_ACCEL_BVH: CUDA events around every launch; fills the *_ms split of ert_stats */
