@@ -319,3 +319,83 @@ def test_committed_synthetic_golden_fixture(gpu):
             assert rgb8.reshape(-1).tolist() == img["rgb8"], (key, accel)
             assert st["rays"] == img["rays"], (key, accel)
         dev.close()
+
+
+# ---- the FP32 triage of shadow rays (shadow_blocked in ert_wavefront.cuh) ---------------------------------------
+def _lights(rows):
+    lights = np.zeros(len(rows), dtype=_lib.LIGHT_DT)
+    for k, (loc, col) in enumerate(rows):
+        lights[k]['location'] = loc
+        lights[k]['diffuse_colour'] = col
+        lights[k]['specular_colour'] = (1, 1, 1)
+    return lights
+
+
+@pytest.mark.parametrize("case", ("c3", "lights_among_the_spheres", "far_and_unrounded_lights", "large_coordinates",
+                                  "double_centres", "radii_over_four_decades", "touching_pairs", "skew_plane"))
+def test_shadow_triage_equals_the_literal_shadow_path(gpu, case):
+    """A shadow ray the triage declares blocked must be one the literal path (FP64 direction, literal tests, here
+    with the shadow rays walking the BVH: ERT_FLAG_NO_LIGHT_GRID) finds blocked: frames and ray counts are equal,
+    on scenes that push the triage's margins — lights a hair's breadth from spheres, lights whose coordinates are
+    not float32 values, coordinates around 1e4, centres that are not float32 values, radii from 0.01 to 100,
+    occluders that touch their targets, an un-normalised plane."""
+    w, h, depth = 320, 180, 4
+    if case == "c3":
+        flat = sc.synthetic_scene("c3")
+        w, h = 960, 540
+    elif case == "lights_among_the_spheres":
+        flat = sc.synthetic_scene("c3", n_spheres=6000)
+        c, r = flat.spheres['center'], flat.spheres['radius']
+        rows = []
+        for k, s in enumerate((11, 222, 3333, 4444)):
+            # just outside sphere s, along a diagonal: 1.0005 r, 1.02 r, 1.5 r, 3 r from its centre
+            d = np.array([0.6, -0.64, 0.48]) * r[s] * (1.0005, 1.02, 1.5, 3.0)[k]
+            rows.append((tuple(c[s] + d), (1.0, 0.3 + 0.2 * k, 0.9 - 0.2 * k)))
+        flat = _with_extras(flat, lights=_lights(rows))
+    elif case == "far_and_unrounded_lights":
+        flat = sc.synthetic_scene("c3", n_spheres=5000)
+        flat = _with_extras(flat, lights=_lights([((1234.56789, -9876.54321, -4321.123456789), (1, 1, 1)),
+                                                   ((0.1, -40.7, 33.3), (1, 0.5, 0.2)),
+                                                   ((-1e4 / 3, -1e3 / 7, 5e3 / 9), (0.2, 0.6, 1.0))]))
+    elif case == "large_coordinates":
+        flat = stress_scene(6000, 6, (40, 20, 40), (0.1, 0.8), scale=100.0, offset=(9000.0, -3000.0, 20000.0))
+        flat = _with_extras(flat, lights=_lights([((9500.0, -8000.0, 15000.0), (1, 1, 0.5)),
+                                                   ((6000.1, -3500.7, 21000.3), (1, 0, 0.5))]))
+        cam = sc.pose_camera(0)
+        cam.location[:] = (9000.0, -3500.0, 14000.0)
+        cam.screen_width, cam.screen_height = 4.0, 2.25
+        flat.camera = cam
+    elif case == "double_centres":
+        flat = stress_scene(5000, 7, (30, 15, 30), (0.05, 0.7), offset=(0.1, -17.3, 40.7), float_exact=False)
+    elif case == "radii_over_four_decades":
+        flat = stress_scene(4000, 21, (40, 15, 40), (0.2, 0.6), offset=(0, -16, 45))
+        rng = np.random.default_rng(21)
+        flat.spheres['radius'] = (10.0 ** rng.uniform(-2, 0.3, len(flat.spheres))).astype(np.float32).astype(np.float64)
+        flat.spheres['radius'][:3] = (100.0, 30.0, 12.0)
+        flat.spheres['center'][:3] = [(0, -140, 160), (-60, -40, 90), (45, -20, 70)]
+    elif case == "touching_pairs":
+        flat = stress_scene(3000, 22, (35, 12, 35), (0.3, 0.7), offset=(0, -14, 45))
+        c, r = flat.spheres['center'], flat.spheres['radius']
+        # every second sphere touches (or slightly overlaps) its predecessor, on the side of the first light
+        to_light = np.array([5.0, -20.0, 0.0]) - c[0::2]
+        to_light /= np.linalg.norm(to_light, axis=1, keepdims=True)
+        c[1::2] = c[0::2] + to_light * ((r[0::2] + r[1::2]) * np.where(np.arange(len(c) // 2) % 2 == 0, 1.0, 0.98))[:, None]
+        flat.spheres['center'] = c
+    else:
+        flat = sc.synthetic_scene("c3", n_spheres=4000)
+        planes = np.zeros(2, dtype=_lib.PLANE_DT)
+        planes['normal'] = [(0, -1, 0), (0.3, -2.5, 0.4)]
+        planes['distance'] = [5, 40]
+        planes['material']['colour'] = [(1, 1, 1), (0.4, 0.8, 0.9)]
+        planes['material']['specular_power'] = [1, 4]
+        planes['material']['shininess'] = [0, 0.5]
+        planes['material']['reflectivity'] = [0.01, 0.6]
+        flat = _with_extras(flat, planes=planes)
+    dev = flat.upload(0)
+    cam = getattr(flat, "camera", None) if case == "large_coordinates" else None
+    a, sa = dev.render(w, h, depth, fmt="f64", accel="auto", camera=cam, flags=_lib.FLAG_COUNT_TESTS)
+    b, sb = dev.render(w, h, depth, fmt="f64", accel="auto", camera=cam, flags=_lib.FLAG_NO_LIGHT_GRID)
+    assert np.array_equal(a, b), case
+    assert sa["rays"] == sb["rays"] and sa["rays"] > 2 * w * h
+    assert sa["gpu_launches"] < sb["gpu_launches"]          # one launch for shadow rays and fold against two or more
+    dev.close()

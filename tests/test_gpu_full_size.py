@@ -107,3 +107,21 @@ def test_c5_8k_row_band_parts_assemble_the_frame(gpu, n_parts):
     assert rays == st["rays"]
     frame.close()
     dev.close()
+
+
+@pytest.mark.parametrize("kind", ("c3", "c4"))
+def test_4k_shadow_triage_equals_the_literal_shadow_path(gpu, kind):
+    """Every shadow ray of the full-size frames (76 M on C3, 102 M on C4): the default path (direction grids, FP32
+    triage, packed literal path, fused fold) against shadow rays that walk the BVH on the literal path."""
+    flat = sc.synthetic_scene(kind)
+    dev = flat.upload(0)
+    a, sa = dev.render(W4K, H4K, 5, fmt="rgb8", accel="auto")
+    b, sb = dev.render(W4K, H4K, 5, fmt="rgb8", accel="auto", flags=_lib.FLAG_NO_LIGHT_GRID)
+    assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
+    # and the unclamped doubles of every fourth row
+    a64 = np.zeros((H4K, W4K, 3), dtype=np.float64)
+    b64 = np.zeros((H4K, W4K, 3), dtype=np.float64)
+    dev.render(W4K, H4K, 5, fmt="f64", accel="auto", band_rows=1, n_parts=4, part=1, out=a64)
+    dev.render(W4K, H4K, 5, fmt="f64", accel="auto", band_rows=1, n_parts=4, part=1, flags=_lib.FLAG_NO_LIGHT_GRID, out=b64)
+    assert np.array_equal(a64, b64) and np.any(a64[1::4] != 0)
+    dev.close()
