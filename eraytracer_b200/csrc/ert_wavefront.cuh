@@ -484,6 +484,7 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
 {
     const DevScene::CellGridDev &cg = sc.cg;
     const uint4 *blk = cg.blocks + (size_t)cell * kBlockU4;
+    WF_ASSERT(cell >= 0 && cell < cg.rx * cg.ry * cg.rz, "cell %d of %d", cell, cg.rx * cg.ry * cg.rz);
     PROBE(0, surv ? 1 : 0);
     PROBE(1, __popc(surv));
     while (surv) {
@@ -501,6 +502,7 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
             fs = __ldg(cg.over_filter + e);
         }
         if (sph < 0) continue;                           // padding (only a NaN ray gets here)
+        WF_ASSERT(sph < sc.n_spheres, "sphere %d of %d (cell %d, bit %d)", sph, sc.n_spheres, cell, k);
         const int code = obj_code(OBJ_SPHERE, sph);
         if (code == skip_obj || code == best.obj) { PROBE(2, 1); continue; }
         {
@@ -1789,6 +1791,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
 #endif
             }
             int at = reserve(__popc(open), n_list);
+            WF_ASSERT(n_list <= (int)(kWfChunk * kSsMaxLights) && nb <= (int)kWfChunk, "list %d chunk %d", n_list, nb);
             while (open) {
                 const int l = __ffs((int)open) - 1;
                 open &= open - 1u;
@@ -1803,6 +1806,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             if (k < n_list) {
                 const unsigned int pr = sh_list[k];
                 const int slot = (int)(pr >> 3), l = (int)(pr & 7u);
+                WF_ASSERT(slot < nb && l < L, "pair %u of chunk %d, %d lights", pr, nb, L);
                 const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
                 const d3 Ph = mk(q0.x, q0.y, q0.z);
                 const int tgt = (int)(__double_as_longlong(q0.w) & 0xffffffffll);
@@ -1846,6 +1850,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             const int k = k0 + lane;
             if (k < n_list) {
                 const int slot = (int)sh_list[k];
+                WF_ASSERT(slot < nb, "slot %d of chunk %d", slot, nb);
                 const unsigned int litmask = sh_lit[slot];
                 const size_t h = (size_t)begin + slot;
                 const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
