@@ -114,6 +114,7 @@ struct ert_scene {
     int device = 0;
     int wf_grid[7] = {0, 0, 0, 0, 0, 0, 0};   // persistent grid sizes: path(first), path, shadow, shade, cell-grid path(first), path, shadow+shade
     int wf_grid_scan = 0;              // brute-force scan kernels (2 blocks per SM)
+    int wf_grid_fin = 0;               // wf_finalize: a streaming pass, every resident slot filled
     HostScene host;
     DevScene dev{};
     std::vector<void *> allocs;
@@ -470,6 +471,8 @@ int upload_scene(ert_scene *s)
         s->wf_grid[1] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path<true, false, true, true>, kWfThreads, 0));
         s->wf_grid[4] = prop.multiProcessorCount * std::max(nb, 1);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_finalize, kWfThreads, 0));
+        s->wf_grid_fin = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_path_refill<false, true, true>, kWfThreads, 0));
         s->wf_grid[5] = prop.multiProcessorCount * std::max(nb, 1);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_trace_shadow<false, true>, kWfThreads, 0));
@@ -728,7 +731,8 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     TICK(-1);
     const DevScene &d = s->dev;
     CU(cudaMemsetAsync(wf.ctr, 0, (size_t)fp.depth * kWfCtr * sizeof(unsigned int), st));
-    CU(cudaMemsetAsync(wf.C, 0, (size_t)wf.n_pad * 3 * sizeof(double), st));
+    // the brute-force scan starts from a cleared colour buffer; the path kernels of bounce 0 clear it themselves
+    if (scan || fp.depth <= 0) CU(cudaMemsetAsync(wf.C, 0, (size_t)wf.n_pad * 3 * sizeof(double), st));
     uint64_t n = 0;
     // ERT_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
     static const bool debug_sync = getenv("ERT_DEBUG_SYNC") != nullptr;
@@ -874,7 +878,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
         WF_CHECK("wf_shade");
     }
     if (overlap && last_shaded >= 0) CU(cudaStreamWaitEvent(st, sl.ev_shade[(size_t)last_shaded], 0));
-    wf_finalize<<<s->wf_grid[3], kWfThreads, 0, st>>>(fp, wf);
+    wf_finalize<<<s->wf_grid_fin, kWfThreads, 0, st>>>(fp, wf);
     n++;
     TICK(2);
     sl.wf_levels = std::min(fp.depth, (int)ERT_MAX_BOUNCE_STATS);

@@ -1106,6 +1106,12 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
             bool walking = false, searched = false;
             int skip = -1;
             if (in_range) {
+                if constexpr (FIRST) {
+                    // the pixel's colour starts at +0.0 (the frame's first launch visits every pixel exactly once:
+                    // no separate 200 MB memset in front of the frame)
+                    const size_t np = (size_t)wf.n_pad;
+                    wf.C[i] = 0.0; wf.C[np + i] = 0.0; wf.C[2 * np + i] = 0.0;
+                }
                 d3 O = mk(0, 0, 0), D = mk(0, 0, 1);
                 path_ray_of_index(fp, wf, FIRST, i, O, D, pid, valid);
                 if (valid) {
