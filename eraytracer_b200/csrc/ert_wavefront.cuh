@@ -1017,6 +1017,9 @@ __device__ __forceinline__ void emit_hits_and_rays(const DevScene &sc, const Fra
 // queue entries at a time (one atomic per chunk) and works through it in batches of 32, so the
 // rays a lane sees one after another are 32 entries apart in the (binned) queue: neighbours in
 // space.  That is what makes the previous ray's sphere a good first guess for the next one.
+#ifndef ERT_WF_HINT_ALL
+#define ERT_WF_HINT_ALL 0            /* 0: only primary rays try the sphere their lane's previous ray hit first */
+#endif
 #ifndef ERT_WF_CHUNK
 #define ERT_WF_CHUNK 128
 #endif
@@ -1121,7 +1124,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     make_sray(sc, O, D, f, a, inv);
                     ray.put(O, D, a, inv);
                     if (sc.n_spheres > 0) {
-                        if (hint >= 0) {
+                        if (hint >= 0 && (FIRST || ERT_WF_HINT_ALL)) {
                             // seed the search with the previous ray's sphere: a real candidate of the
                             // scan, so the minimum over (t, order) is unchanged
                             double t;
