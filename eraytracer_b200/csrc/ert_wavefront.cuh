@@ -183,9 +183,6 @@ __device__ __forceinline__ void make_sray(const DevScene &sc, d3 O, d3 D, SRay &
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifndef ERT_GRID_PREFETCH
-#define ERT_GRID_PREFETCH 3            /* 0: both blocks of the next cell to L1, 1: L1 + L2, 2: both to L2, 3: first block to L1 only — all within 0.4 % on C4 */
-#endif
 __device__ __forceinline__ void ldg256(const void *p, float (&v)[8])
 {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -564,18 +561,8 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         TALLY(cell);
         te = grid_advance(g, r, cg);
         if (g.id >= 0 && !(te > g.cullk)) {
-#if ERT_GRID_PREFETCH == 0
+            // (to L1 or to L2, one block or both: within 0.4 % of one another on C4 — DESIGN.md "dropped")
             prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
-            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4 + 8);
-#elif ERT_GRID_PREFETCH == 1
-            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
-            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4 + 8);
-#elif ERT_GRID_PREFETCH == 2
-            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4);
-            prefetch_l2(cg.blocks + (size_t)g.id * kBlockU4 + 8);
-#else
-            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
-#endif
         }
         if (hd.x) break;
         if (te > g.cullk) { g.id = -1; return false; }
@@ -1017,9 +1004,6 @@ __device__ __forceinline__ void emit_hits_and_rays(const DevScene &sc, const Fra
 // queue entries at a time (one atomic per chunk) and works through it in batches of 32, so the
 // rays a lane sees one after another are 32 entries apart in the (binned) queue: neighbours in
 // space.  That is what makes the previous ray's sphere a good first guess for the next one.
-#ifndef ERT_WF_HINT_ALL
-#define ERT_WF_HINT_ALL 0            /* 0: only primary rays try the sphere their lane's previous ray hit first */
-#endif
 #ifndef ERT_WF_CHUNK
 #define ERT_WF_CHUNK 128
 #endif
@@ -1056,12 +1040,8 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 // A warp that has taken the chunk [begin, end) of the path queue asks L2 for its lines: the rays of a chunk are
 // handed out a few at a time as lanes finish, and each hand-out would otherwise wait for HBM with the whole
 // warp standing still.  Eight arrays (origin, direction, weight, pixel), sixteen entries per line.
-#ifndef ERT_WF_PREFETCH_CHUNK
-#define ERT_WF_PREFETCH_CHUNK 1
-#endif
 __device__ __forceinline__ void prefetch_path_chunk(const WfBuf &wf, unsigned long long begin, unsigned long long end, int lane)
 {
-#if ERT_WF_PREFETCH_CHUNK
     const size_t np = (size_t)wf.n_pad;
     const int arr = lane & 7;
     for (unsigned long long e = begin + (unsigned long long)((lane >> 3) * 16); e < end; e += 64) {
@@ -1069,7 +1049,6 @@ __device__ __forceinline__ void prefetch_path_chunk(const WfBuf &wf, unsigned lo
                                 : (arr == 6 ? (const void *)(wf.q_w + e) : (const void *)(wf.q_pid + e));
         prefetch_l2(p);
     }
-#endif
 }
 
 // Path rays of one bounce: nearest_object_intersecting_ray/2 (erl:300-346) for every ray of
@@ -1124,7 +1103,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                     make_sray(sc, O, D, f, a, inv);
                     ray.put(O, D, a, inv);
                     if (sc.n_spheres > 0) {
-                        if (hint >= 0 && (FIRST || ERT_WF_HINT_ALL)) {
+                        if (FIRST && hint >= 0) {                     // first reflections have too little in common (measured: 7.505 vs 7.487 ms)
                             // seed the search with the previous ray's sphere: a real candidate of the
                             // scan, so the minimum over (t, order) is unchanged
                             double t;
@@ -1741,9 +1720,6 @@ __device__ __forceinline__ bool shadow_blocked(const DevScene &sc, const LightGr
 #ifndef ERT_SS_MINBLOCKS
 #define ERT_SS_MINBLOCKS 4
 #endif
-#ifndef ERT_SS_TRIAGE
-#define ERT_SS_TRIAGE 1
-#endif
 constexpr int kSsMaxLights = 8;                  // three bits of a pair's entry; ert_api.cu uses the kernel for <= 8 lights
 static_assert(kWfChunk <= 128, "a chunk's hits are numbered with seven bits");
 template <bool COUNT>
@@ -1787,7 +1763,6 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
                 rays += (unsigned int)L;
                 sh_lit[slot] = 0u;
-#if ERT_SS_TRIAGE
                 const d3 P = mk(r0.x, r0.y, r0.z);
                 const int target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
                 float4 tf = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1795,9 +1770,6 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 for (int l = 0; l < L; l++) {
                     if (!shadow_blocked(sc, sc.lgrids[l], sc.lights + 9 * (size_t)l, P, target, tf)) open |= 1u << l;
                 }
-#else
-                open = (1u << L) - 1u;
-#endif
             }
             int at = reserve(__popc(open), n_list);
             WF_ASSERT(n_list <= (int)(kWfChunk * kSsMaxLights) && nb <= (int)kWfChunk, "list %d chunk %d", n_list, nb);
