@@ -1,17 +1,22 @@
-// Wavefront form of the eraytracer hot path for large sphere counts (ERT_ACCEL_BVH).
+// Wavefront form of the eraytracer hot path for large sphere counts (ERT_ACCEL_BVH, ERT_ACCEL_GRID).
 //
 // The per-pixel recursion of raytracer.erl:186-252 is cut into queues that live in HBM, so
 // that every traversal warp is full of live rays of ONE kind:
 //
-//   bounce b:  wf_trace_path    path queue  -> nearest hit (erl:300-346) -> hit queue (compacted)
-//              wf_trace_shadow  hit queue x lights -> shadow_factor (erl:256-267) -> lit flags
-//              wf_shade         hit queue + lit flags -> colour accumulation (erl:209-252)
-//                                                     -> path queue of bounce b+1 (compacted)
-//   end:       wf_finalize      colour -> framebuffer (quantisation of erl:678-680 fused)
+//   bounce b:  wf_trace_path[_refill]  path queue -> nearest hit (erl:300-346) -> hit record (compacted) AND the
+//                                      reflection ray of bounce b+1 (erl:219-221), written by the same warp
+//              wf_shadow_shade         hit queue x lights -> shadow_factor (erl:256-267: FP32 triage, then the literal
+//                                      path for the pairs it leaves open) -> light fold into the pixel (erl:209-252);
+//                                      on a second stream, beside the path rays of bounce b+1
+//   end:       wf_finalize             colour -> framebuffer (quantisation of erl:678-680 fused)
+//
+// (wf_emit_hits, wf_bin_*, wf_trace_shadow and wf_shade are the same stages as separate launches: used when the
+// hits are binned by location or a light has no direction grid.)
 //
 // The arithmetic is the megakernel's (ert_device.cuh): FP64 in the literal operation order for
-// everything that feeds a decision or a colour, FP32 only in conservative filters.  Both forms
-// produce bit-identical frames (tests/test_gpu_parity.py).
+// everything that feeds a decision or a colour, FP32 only in conservative filters and in proofs with explicit
+// margins (shadow_blocked).  All forms produce bit-identical frames (tests/test_gpu_parity.py, test_gpu_edges.py,
+// test_gpu_cell_grid.py).
 #pragma once
 
 #include <limits.h>
