@@ -85,3 +85,19 @@ def assert_double_parity(gpu, ref, rtol=1e-9, atol=1e-12):
     assert not bad.any(), ("%d channel values differ, worst %.3e at %s"
                            % (int(bad.sum()), float(err.max()),
                               np.unravel_index(int(err.argmax()), err.shape)))
+
+
+def clustered_scene():
+    """3000 ordinary spheres plus a knot of 70 small ones inside one cell of the cell grid: that cell's list runs
+    through both of its blocks, the overflow groups and more than one survivor mask (32 < count <= 127)."""
+    from eraytracer_b200 import scene as sc
+    rng = np.random.default_rng(31)
+    flat = sc.synthetic_scene("c3", n_spheres=3000, seed=31)
+    c = np.stack([rng.uniform(-b, b, 3000) for b in (30, 12, 30)], axis=1) + np.asarray((0.0, -14.0, 45.0))
+    r = rng.uniform(0.2, 0.6, 3000)
+    knot = np.array([3.3, -13.1, 44.2]) + rng.uniform(-0.35, 0.35, (70, 3))
+    c[:70] = knot
+    r[:70] = rng.uniform(0.03, 0.08, 70)
+    flat.spheres['center'] = c.astype(np.float32).astype(np.float64)
+    flat.spheres['radius'] = r.astype(np.float32).astype(np.float64)
+    return flat, flat.spheres['center'][:70].copy()

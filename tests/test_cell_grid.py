@@ -337,6 +337,19 @@ def test_packed_blocks_hold_the_same_lists(cg, density):
     g.close()
 
 
+def test_clustered_scene_keeps_its_grid_and_has_a_long_cell_list(cg):
+    """CPU side of tests/test_gpu_cell_grid.py::test_long_cell_lists_equal_the_linear_scan: the builder keeps the
+    grid for the scene with a knot of 70 small spheres, and some cell lists more than 32 of them (so the device
+    walk goes through both blocks, the overflow groups and more than one survivor mask)."""
+    from helpers import clustered_scene
+    flat, knot = clustered_scene()
+    g = Grid(cg, flat.spheres['center'], flat.spheres['radius'])
+    assert g.enabled
+    counts = g.cells & 127
+    assert 32 < counts.max() <= 127
+    g.close()
+
+
 def test_far_origins_are_refused(cg):
     rng = np.random.default_rng(6)
     c, r = rand_scene(rng, 3000, (30, 12, 30), 0.2, 0.7, offset=(0, -10, 40))

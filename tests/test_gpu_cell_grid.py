@@ -8,7 +8,7 @@ import pytest
 import eraytracer_b200 as ert
 from eraytracer_b200 import _lib, multigpu, scene as sc
 from oracle import orc
-from helpers import assert_double_parity, oracle_frame, oracle_scene_from_flat, quantise
+from helpers import assert_double_parity, clustered_scene, oracle_frame, oracle_scene_from_flat, quantise
 
 pytestmark = pytest.mark.gpu
 
@@ -398,4 +398,28 @@ def test_shadow_triage_equals_the_literal_shadow_path(gpu, case):
     assert np.array_equal(a, b), case
     assert sa["rays"] == sb["rays"] and sa["rays"] > 2 * w * h
     assert sa["gpu_launches"] < sb["gpu_launches"]          # one launch for shadow rays and fold against two or more
+    dev.close()
+
+
+def test_long_cell_lists_equal_the_linear_scan(gpu):
+    flat, knot = clustered_scene()
+    dev = flat.upload(0)
+    rng = np.random.default_rng(5)
+    # rays aimed at the knot from all around, and rays that start inside it
+    o = knot.mean(axis=0) + rng.normal(size=(40_000, 3)) * 6.0
+    t = knot[rng.integers(0, 70, 40_000)] + rng.normal(size=(40_000, 3)) * 0.05
+    d = t - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([np.concatenate([o, d], axis=1),
+                           random_rays(rng, 10_000, knot.min(axis=0) - 0.2, knot.max(axis=0) + 0.2)], axis=0)
+    og, tg = dev.trace_rays(rays, accel="grid")
+    ol, tl = dev.trace_rays(rays, accel="linear")
+    assert np.array_equal(og, ol) and np.array_equal(tg, tl)
+    assert (og >= 0).mean() > 0.8 and (og[:40_000] < 73).mean() > 0.3          # many of them hit the knot
+    cam = sc.pose_camera(0)
+    cam.location[:] = (3.3, -13.1, 40.0)
+    cam.screen_width, cam.screen_height = 1.0, 0.5625
+    a, sa = dev.render(320, 180, 4, fmt="f64", accel="grid", camera=cam)
+    b, sb = dev.render(320, 180, 4, fmt="f64", accel="bvh", camera=cam, flags=_lib.FLAG_NO_LIGHT_GRID)
+    assert sa["accel_used"] == "grid" and np.array_equal(a, b) and sa["rays"] == sb["rays"]
     dev.close()
