@@ -226,7 +226,8 @@ ERT_API int ert_get_stats(ert_scene *scene, int slot, ert_stats *out);
 
 /* Nearest object for a batch of rays (origin xyz, direction xyz as doubles):
  * nearest_object_intersecting_ray/2 (erl:300-302).  order_out[i] is the list
- * position of the nearest object or -1 for 'none'; t_out[i] its Distance. */
+ * position of the nearest object or -1 for 'none'; t_out[i] its Distance.
+ * The device time of the kernel is left in slot 0's stats (ert_get_stats(scene, 0, ..).kernel_ms). */
 ERT_API int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int accel,
                    int32_t *order_out, double *t_out);
 
