@@ -143,6 +143,25 @@ __device__ __forceinline__ d3 vbounce(d3 v, d3 n) { return vadd(vscale(n, 2.0 * 
 // lists:max([0, X]) erl:275, 290
 __device__ __forceinline__ double max0(double x) { return x > 0.0 ? x : 0.0; }
 
+// 32-byte records in ONE 256-bit transaction (LDG.E.256 / STG.E.256, sm_100): an FP64 sphere {cx, cy, cz, r}
+// (read-only for the life of a kernel), and the queue records one kernel writes for the next.
+__device__ __forceinline__ double4 ld_sphere(const double4 *p)
+{
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double4 ld_rec32(const void *p)
+{
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_rec32(void *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 struct Hit {
     double t;
     int order;     // list position of the object
@@ -293,7 +312,7 @@ __device__ __forceinline__ bool object_exact(const DevScene &sc, int code, d3 O,
 {
     int i = obj_index(code);
     switch (obj_type(code)) {
-    case OBJ_SPHERE: return sphere_exact(O, D, a, sc.sph_exact[i], t);
+    case OBJ_SPHERE: return sphere_exact(O, D, a, ld_sphere(sc.sph_exact + i), t);
     case OBJ_PLANE: return plane_exact(O, D, sc.planes + 4 * i, t);
     default: return triangle_exact(O, D, sc.tris + 9 * i, t);
     }
@@ -410,7 +429,7 @@ __device__ __forceinline__ void try_sphere(const DevScene &sc, const FRay &f, d3
     if (code == skip_obj) return;
     double t;
     TALLY(exact_sph);
-    if (sphere_exact(O, D, f.a, sc.sph_exact[sph], t)) {
+    if (sphere_exact(O, D, f.a, ld_sphere(sc.sph_exact + sph), t)) {
         int ord = sc.sph_order[sph];
         if (better(t, ord, best)) {
             best.t = t; best.order = ord; best.obj = code;
@@ -433,7 +452,7 @@ __device__ __forceinline__ void scan_spheres_exact(const DevScene &sc, d3 O, d3 
         if (code == skip_obj) continue;
         double t;
         TALLY(exact_sph);
-        if (sphere_exact(O, D, a, sc.sph_exact[s], t)) {
+        if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + s), t)) {
             int ord = sc.sph_order[s];
             if (better(t, ord, best)) { best.t = t; best.order = ord; best.obj = code; }
         }
@@ -604,7 +623,7 @@ __device__ __forceinline__ d3 hit_normal(const DevScene &sc, int obj, d3 P)
     int i = obj_index(obj);
     switch (obj_type(obj)) {
     case OBJ_SPHERE: {
-        double4 s = sc.sph_exact[i];
+        double4 s = ld_sphere(sc.sph_exact + i);
         return vnormalize(vsub(P, mk(s.x, s.y, s.z)));
     }
     case OBJ_PLANE:
@@ -908,7 +927,7 @@ render_tiled_kernel(const __grid_constant__ DevScene sc, const __grid_constant__
                             if (code != skip) {
                                 double tt;
                                 TALLY(exact_sph);
-                                if (sphere_exact(q.O, q.D, f.a, sc.sph_exact[sph], tt)) {
+                                if (sphere_exact(q.O, q.D, f.a, ld_sphere(sc.sph_exact + sph), tt)) {
                                     int ord = sc.sph_order[sph];
                                     if (better(tt, ord, q.best)) {
                                         q.best.t = tt; q.best.order = ord; q.best.obj = code;

@@ -98,7 +98,7 @@ __device__ __forceinline__ void scan_ray_of_index(const DevScene &sc, const Fram
     if constexpr (SHADOW) {
         l = (unsigned int)(i / n_hits);
         h = (unsigned int)(i - (unsigned long long)l * n_hits);
-        const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+        const double4 r0 = ld_rec32(wf.hit_head + h);
         const d3 P = mk(r0.x, r0.y, r0.z);
         target = (int)(__double_as_longlong(r0.w) & 0xffffffffll);
         target_order = (int)(__double_as_longlong(r0.w) >> 32);
@@ -173,7 +173,7 @@ __device__ __noinline__ void scan_resolve(const DevScene *scp, const FrameParams
     if (SHADOW && code == target) return;
     const double a = D.x * D.x + D.y * D.y + D.z * D.z;
     double t;
-    if (!sphere_exact(O, D, a, sc.sph_exact[sph], t)) return;
+    if (!sphere_exact(O, D, a, ld_sphere(sc.sph_exact + sph), t)) return;
     const int ord = sc.sph_order[sph];
     if constexpr (SHADOW) {
         Hit tg;

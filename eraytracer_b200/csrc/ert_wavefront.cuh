@@ -231,7 +231,7 @@ __device__ __forceinline__ void leaf_sphere(const DevScene &sc, const SRay &f, c
     if (code == skip_obj) return;
     double t;
     TALLY(exact_sph);
-    if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+    if (sphere_exact(ray.O(), ray.D(), ray.a(), ld_sphere(sc.sph_exact + sph), t)) {
         int ord = sc.sph_order[sph];
         if (better(t, ord, best)) {
             best.t = t; best.order = ord; best.obj = code;
@@ -466,11 +466,16 @@ __device__ __forceinline__ unsigned int grid_filter_over(const DevScene &sc, con
     const float4 *fp4 = sc.cg.over_filter + e0;
     const float nth = -f.theta, nbc = -f.bcull;
     unsigned int surv = 0u;
-    float4 s0 = __ldg(fp4), s1 = __ldg(fp4 + 1), s2 = __ldg(fp4 + 2), s3 = __ldg(fp4 + 3);
+    float p[8], q[8];
+    ldg256(fp4, p); ldg256(fp4 + 2, q);                  // groups of four are 64-byte aligned: two 256-bit loads
+    float4 s0 = make_float4(p[0], p[1], p[2], p[3]), s1 = make_float4(p[4], p[5], p[6], p[7]);
+    float4 s2 = make_float4(q[0], q[1], q[2], q[3]), s3 = make_float4(q[4], q[5], q[6], q[7]);
 #pragma unroll 1
     for (int k = 0; k < cnt; k += 4) {
         // the next group is in flight while this one is tested (one group past the list at the end: it exists)
-        const float4 n0 = __ldg(fp4 + k + 4), n1 = __ldg(fp4 + k + 5), n2 = __ldg(fp4 + k + 6), n3 = __ldg(fp4 + k + 7);
+        ldg256(fp4 + k + 4, p); ldg256(fp4 + k + 6, q);
+        const float4 n0 = make_float4(p[0], p[1], p[2], p[3]), n1 = make_float4(p[4], p[5], p[6], p[7]);
+        const float4 n2 = make_float4(q[0], q[1], q[2], q[3]), n3 = make_float4(q[4], q[5], q[6], q[7]);
         const unsigned int m = stage1_bit(f, s0, nth, nbc) | (stage1_bit(f, s1, nth, nbc) << 1) |
                                (stage1_bit(f, s2, nth, nbc) << 2) | (stage1_bit(f, s3, nth, nbc) << 3);
         surv |= m << (kGridInline + k);
@@ -514,7 +519,7 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
         }
         double t;
         TALLY(exact_sph);
-        if (sphere_exact(ray.O(), ray.D(), ray.a(), sc.sph_exact[sph], t)) {
+        if (sphere_exact(ray.O(), ray.D(), ray.a(), ld_sphere(sc.sph_exact + sph), t)) {
             PROBE(5, 1);
             // better() of erl:319 with the list positions fetched only for a tie
             bool win = best.obj < 0 || t < best.t;
@@ -557,12 +562,12 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         blk = cg.blocks + (size_t)cell * kBlockU4;
         // one 128-byte line: count and overflow word, six filter spheres
         hd = __ldg(reinterpret_cast<const uint2 *>(blk) + 15);
-        s0 = __ldg(reinterpret_cast<const float4 *>(blk));
-        s1 = __ldg(reinterpret_cast<const float4 *>(blk) + 1);
-        s2 = __ldg(reinterpret_cast<const float4 *>(blk) + 2);
-        s3 = __ldg(reinterpret_cast<const float4 *>(blk) + 3);
-        s4 = __ldg(reinterpret_cast<const float4 *>(blk) + 4);
-        s5 = __ldg(reinterpret_cast<const float4 *>(blk) + 5);
+        {
+            float p[8];
+            ldg256(blk, p);     s0 = make_float4(p[0], p[1], p[2], p[3]); s1 = make_float4(p[4], p[5], p[6], p[7]);
+            ldg256(blk + 2, p); s2 = make_float4(p[0], p[1], p[2], p[3]); s3 = make_float4(p[4], p[5], p[6], p[7]);
+            ldg256(blk + 4, p); s4 = make_float4(p[0], p[1], p[2], p[3]); s5 = make_float4(p[4], p[5], p[6], p[7]);
+        }
         TALLY(cell);
         te = grid_advance(g, r, cg);
         if (g.id >= 0 && !(te > g.cullk)) {
@@ -580,12 +585,12 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
            (stage1_bit(f, s3, nth, nbc) << 3) | (stage1_bit(f, s4, nth, nbc) << 4) | (stage1_bit(f, s5, nth, nbc) << 5);
     if (cnt > kCellGridInline) {
         // the second block of the cell (asked for a step ago, like the first)
-        s0 = __ldg(reinterpret_cast<const float4 *>(blk) + 8);
-        s1 = __ldg(reinterpret_cast<const float4 *>(blk) + 9);
-        s2 = __ldg(reinterpret_cast<const float4 *>(blk) + 10);
-        s3 = __ldg(reinterpret_cast<const float4 *>(blk) + 11);
-        s4 = __ldg(reinterpret_cast<const float4 *>(blk) + 12);
-        s5 = __ldg(reinterpret_cast<const float4 *>(blk) + 13);
+        {
+            float p[8];
+            ldg256(blk + 8, p);  s0 = make_float4(p[0], p[1], p[2], p[3]); s1 = make_float4(p[4], p[5], p[6], p[7]);
+            ldg256(blk + 10, p); s2 = make_float4(p[0], p[1], p[2], p[3]); s3 = make_float4(p[4], p[5], p[6], p[7]);
+            ldg256(blk + 12, p); s4 = make_float4(p[0], p[1], p[2], p[3]); s5 = make_float4(p[4], p[5], p[6], p[7]);
+        }
         surv |= (stage1_bit(f, s0, nth, nbc) << 6) | (stage1_bit(f, s1, nth, nbc) << 7) | (stage1_bit(f, s2, nth, nbc) << 8) |
                 (stage1_bit(f, s3, nth, nbc) << 9) | (stage1_bit(f, s4, nth, nbc) << 10) | (stage1_bit(f, s5, nth, nbc) << 11);
         cnt -= kGridInline;
@@ -907,7 +912,7 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
         if (filter_stage1(f, fs, fb, fv) && obj_code(OBJ_SPHERE, sph) != target && filter_stage2(f, fs, fb, fv, cull0)) {
             double th;
             TALLY(exact_sph);
-            if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+            if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + sph), th) && better(th, sc.sph_order[sph], best)) return true;
         }
         if (!more) break;
     }
@@ -916,7 +921,7 @@ __device__ __forceinline__ bool light_grid_occluded(const DevScene &sc, const Li
         if (obj_code(OBJ_SPHERE, sph) == target) continue;
         double th;
         TALLY(exact_sph);
-        if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) return true;
+        if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + sph), th) && better(th, sc.sph_order[sph], best)) return true;
     }
     return false;
 }
@@ -928,17 +933,12 @@ __device__ __forceinline__ int rank_in(unsigned int m, int lane) { return __popc
 __device__ __forceinline__ void write_hit(HitHead *heads, HitTail *tails, size_t s, d3 P, d3 N, d3 D, int obj, int order,
                                           int pid, double W)
 {
-    HitHead hh;
-    HitTail ht;
-    hh.P[0] = P.x; hh.P[1] = P.y; hh.P[2] = P.z; hh.obj = obj; hh.order = order;
-    ht.N[0] = N.x; ht.N[1] = N.y; ht.N[2] = N.z; ht.pid = pid; ht.pad0 = 0;
-    ht.D[0] = D.x; ht.D[1] = D.y; ht.D[2] = D.z; ht.W = W;
-    const uint4 *sh = reinterpret_cast<const uint4 *>(&hh);
-    const uint4 *st = reinterpret_cast<const uint4 *>(&ht);
-    uint4 *dh = reinterpret_cast<uint4 *>(heads + s);
-    uint4 *dt = reinterpret_cast<uint4 *>(tails + s);
-    dh[0] = sh[0]; dh[1] = sh[1];
-    dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+    // three 256-bit stores: {P, obj | order}, {N, pid}, {D, W}
+    const double oo = __longlong_as_double(((long long)order << 32) | (long long)(unsigned int)obj);
+    const double pp = __longlong_as_double((long long)(unsigned int)pid);
+    st_rec32(heads + s, P.x, P.y, P.z, oo);
+    st_rec32(tails + s, N.x, N.y, N.z, pp);
+    st_rec32(reinterpret_cast<char *>(tails + s) + 32, D.x, D.y, D.z, W);
 }
 
 // The reflection ray of a hit (erl:216-224): leaves the hit location along the bounced direction and carries the
@@ -1114,7 +1114,7 @@ wf_trace_path(const __grid_constant__ DevScene sc, const __grid_constant__ Frame
                             double t;
                             TALLY(exact_sph);
                             PROBE(7, 1);
-                            if (sphere_exact(O, D, a, sc.sph_exact[hint], t)) {
+                            if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + hint), t)) {
                                 int ord = sc.sph_order[hint];
                                 if (better(t, ord, best)) {
                                     best.t = t; best.order = ord; best.obj = obj_code(OBJ_SPHERE, hint);
@@ -1464,7 +1464,7 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             rays++;
             bool lit = false;
             {
-                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+                const double4 r0 = ld_rec32(wf.hit_head + h);
                 // the next batch's record (same light, 32 hits on) and this target's FP64 sphere: on their
                 // way to L1 while the direction is normalised
                 if (h + 32u < n_hits) prefetch_l1(wf.hit_head + h + 32u);
@@ -1486,7 +1486,7 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                     if (lit && hint >= 0 && obj_code(OBJ_SPHERE, hint) != target) {
                         double th;
                         TALLY(exact_sph);
-                        if (sphere_exact(O, D, a, sc.sph_exact[hint], th) && better(th, sc.sph_order[hint], best))
+                        if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + hint), th) && better(th, sc.sph_order[hint], best))
                             lit = false;
                     }
                     if (lit && sc.n_spheres > 0 && USE_GRID && l < (unsigned int)sc.lg_count) {
@@ -1510,7 +1510,7 @@ wf_trace_shadow(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                                 if (obj_code(OBJ_SPHERE, sph) != target) {
                                     double th;
                                     TALLY(exact_sph);
-                                    if (sphere_exact(O, D, a, sc.sph_exact[sph], th) && better(th, sc.sph_order[sph], best)) {
+                                    if (sphere_exact(O, D, a, ld_sphere(sc.sph_exact + sph), th) && better(th, sc.sph_order[sph], best)) {
                                         lit = false;
                                         hint = sph;
                                     }
@@ -1765,7 +1765,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
             const int slot = s0 + lane;
             unsigned int open = 0u;                                  // lights whose ray the triage could not settle
             if (slot < nb) {
-                const double4 r0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
+                const double4 r0 = ld_rec32(wf.hit_head + begin + slot);
                 rays += (unsigned int)L;
                 sh_lit[slot] = 0u;
                 const d3 P = mk(r0.x, r0.y, r0.z);
@@ -1793,7 +1793,7 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 const unsigned int pr = sh_list[k];
                 const int slot = (int)(pr >> 3), l = (int)(pr & 7u);
                 WF_ASSERT(slot < nb && l < L, "pair %u of chunk %d, %d lights", pr, nb, L);
-                const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + begin + slot);
+                const double4 q0 = ld_rec32(wf.hit_head + begin + slot);
                 const d3 Ph = mk(q0.x, q0.y, q0.z);
                 const int tgt = (int)(__double_as_longlong(q0.w) & 0xffffffffll);
                 const int order = (int)(__double_as_longlong(q0.w) >> 32);
@@ -1839,14 +1839,14 @@ wf_shadow_shade(const __grid_constant__ DevScene sc, const __grid_constant__ Fra
                 WF_ASSERT(slot < nb, "slot %d of chunk %d", slot, nb);
                 const unsigned int litmask = sh_lit[slot];
                 const size_t h = (size_t)begin + slot;
-                const double4 q0 = *reinterpret_cast<const double4 *>(wf.hit_head + h);
+                const double4 q0 = ld_rec32(wf.hit_head + h);
                 const d3 P = mk(q0.x, q0.y, q0.z);
                 const int target = (int)(__double_as_longlong(q0.w) & 0xffffffffll);
                 HitTail ht;
                 {
-                    const uint4 *st = reinterpret_cast<const uint4 *>(wf.hit_tail + h);
-                    uint4 *dt = reinterpret_cast<uint4 *>(&ht);
-                    dt[0] = st[0]; dt[1] = st[1]; dt[2] = st[2]; dt[3] = st[3];
+                    const double4 t0 = ld_rec32(wf.hit_tail + h), t1 = ld_rec32(reinterpret_cast<const char *>(wf.hit_tail + h) + 32);
+                    double4 *dt = reinterpret_cast<double4 *>(&ht);
+                    dt[0] = t0; dt[1] = t1;
                 }
                 const int pid = ht.pid;
                 d3 S = mk(0.0, 0.0, 0.0);
