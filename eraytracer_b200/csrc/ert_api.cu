@@ -641,12 +641,13 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf, bool sc
     size_t n_pad = (size_t)tiles_x * (size_t)tiles_y * 32;
     if (n_pad >= ((size_t)1 << 31)) return fail(ERT_ERR_BADARG, "frame part has more than 2^31 pixels");
     size_t L = (size_t)std::max(s->host.n_lights, 1);
-    // layout: C[3] res_t[1] q_ray[6]x2 q_w[1]x2 doubles | hits, raw_hits records | q_pid x2 res_hit[2] r_key ints |
+    // layout: C[3] res_t[1] doubles | two path queues | hits, raw_hits records | res_hit[2] r_key ints |
     // lit bytes | sort histogram + block sums
     size_t off = 0;
-    size_t o_dbl = off; off += align_up(n_pad * 18 * sizeof(double), 256);
+    size_t o_dbl = off; off += align_up(n_pad * 4 * sizeof(double), 256);
+    size_t o_path = off; off += align_up(n_pad * 2 * sizeof(PathRec), 256);
     size_t o_rec = off; off += align_up(n_pad * 2 * (sizeof(HitHead) + sizeof(HitTail)), 256);
-    size_t o_int = off; off += align_up(n_pad * 5 * sizeof(int), 256);
+    size_t o_int = off; off += align_up(n_pad * 3 * sizeof(int), 256);
     size_t o_lit = off; off += align_up(n_pad * L, 256);
     size_t o_hist = off; off += align_up(((size_t)kSortCells + kSortBlocks) * sizeof(unsigned int), 256);
     if (sl.wf_cap < off) {
@@ -673,10 +674,10 @@ int wf_prepare(ert_scene *s, Slot &sl, const FrameParams &fp, WfBuf &wf, bool sc
     wf.n_pad = (int)n_pad;
     wf.tiles_x = tiles_x;
     wf.C = d; wf.res_t = d + 3 * n_pad;
-    wf.q_ray = d + 4 * n_pad; wf.nq_ray = d + 10 * n_pad; wf.q_w = d + 16 * n_pad; wf.nq_w = d + 17 * n_pad;
+    wf.q = (PathRec *)(base + o_path); wf.nq = wf.q + n_pad;
     wf.hit_head = (HitHead *)(base + o_rec); wf.raw_head = wf.hit_head + n_pad;
     wf.hit_tail = (HitTail *)(wf.raw_head + n_pad); wf.raw_tail = wf.hit_tail + n_pad;
-    wf.q_pid = i; wf.nq_pid = i + n_pad; wf.res_hit = (int2 *)(i + 2 * n_pad); wf.r_key = (unsigned int *)(i + 4 * n_pad);
+    wf.res_hit = (int2 *)i; wf.r_key = (unsigned int *)(i + 2 * n_pad);
     wf.lit = base + o_lit;
     wf.hist = (unsigned int *)(base + o_hist);
     wf.sums = wf.hist + kSortCells;
@@ -759,7 +760,7 @@ int launch_wavefront(ert_scene *s, Slot &sl, const FrameParams &fp_in, bool unso
     } while (0)
     const WfBuf wf_even = wf;
     WfBuf wf_odd = wf;
-    std::swap(wf_odd.q_pid, wf_odd.nq_pid); std::swap(wf_odd.q_ray, wf_odd.nq_ray); std::swap(wf_odd.q_w, wf_odd.nq_w);
+    std::swap(wf_odd.q, wf_odd.nq);
     // Two chains per frame.  The reflection rays of bounce b+1 exist as soon as the hits of bounce b do (they do not
     // depend on the shadow rays), so `st` goes straight on to the next bounce's path rays while `st2` answers the
     // shadow rays of bounce b and folds its colours: the tails of the path launches, where a few long walks keep

@@ -157,6 +157,13 @@ __device__ __forceinline__ double4 ld_rec32(const void *p)
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+// the same, read once (evict-first): queue entries must not push the scene out of L1/L2
+__device__ __forceinline__ double4 ld_rec32_cs(const void *p)
+{
+    double4 r;
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void st_rec32(void *p, double a, double b, double c, double d)
 {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");

@@ -54,6 +54,15 @@ struct alignas(32) HitTail {
 };
 static_assert(sizeof(HitHead) == 32 && sizeof(HitTail) == 64, "hit records are 32 + 64 bytes");
 
+// One ray of the path queue: two 256-bit transactions to write, two to read.
+struct alignas(32) PathRec {
+    double O[3];                // origin
+    double W;                   // weight of the path: product of (lights * reflectivity) of earlier bounces
+    double D[3];                // direction
+    int pid, pad0;              // pixel of the path
+};
+static_assert(sizeof(PathRec) == 64, "a path ray is 64 bytes");
+
 // nearest hit of one path ray of the brute-force scan: 16 bytes, one 128-bit compare-and-swap
 struct alignas(16) ScanBest {
     double t;
@@ -67,12 +76,8 @@ struct WfBuf {
     // path queue of the bounce being traced (read) and of the next one (written by whoever emits the hits): two
     // buffer sets that swap every bounce, so that the next rays exist as soon as their hits do — the reflection
     // (erl:219-221) does not depend on the shadow rays, only the colour does
-    int *q_pid;                 // pixel of each ray
-    double *q_ray;              // [6][n_pad] origin xyz, direction xyz
-    double *q_w;                // [n_pad] weight of the path: product of (lights * reflectivity) of earlier bounces
-    int *nq_pid;
-    double *nq_ray;
-    double *nq_w;
+    PathRec *q;                 // [n_pad] rays of the bounce being traced
+    PathRec *nq;                // [n_pad] rays of the next bounce
     double *res_t;              // nearest hit of each path ray: Distance,
     int2 *res_hit;              //   (object code or -1, list position)
     HitHead *hit_head;          // hit queue the shadow and shade stages read
@@ -737,23 +742,25 @@ __device__ __forceinline__ void pixel_of_index(const FrameParams &fp, const WfBu
 
 __device__ __forceinline__ double path_weight_of_index(const WfBuf &wf, bool first, unsigned int i)
 {
-    return first ? 1.0 : __ldcs(wf.q_w + i);
+    return first ? 1.0 : __ldcs(&wf.q[i].W);
 }
 __device__ __forceinline__ void path_ray_of_index(const FrameParams &fp, const WfBuf &wf, bool first, unsigned int i,
-                                                  d3 &O, d3 &D, int &pid, bool &valid)
+                                                  d3 &O, d3 &D, int &pid, bool &valid, double *W_out = nullptr)
 {
     if (first) {
         int X, ly, Y;
         pixel_of_index(fp, wf, (int)i, X, ly, Y, valid);
         pid = (int)i;
         if (valid) primary_ray(fp, X, Y, O, D);                 // erl:486-511
+        if (W_out) *W_out = 1.0;
     } else {
-        const size_t np = (size_t)wf.n_pad;
         valid = true;
-        // queue traffic is read once: streaming loads keep it from evicting the BVH
-        pid = __ldcs(wf.q_pid + i);
-        O = mk(__ldcs(wf.q_ray + i), __ldcs(wf.q_ray + np + i), __ldcs(wf.q_ray + 2 * np + i));
-        D = mk(__ldcs(wf.q_ray + 3 * np + i), __ldcs(wf.q_ray + 4 * np + i), __ldcs(wf.q_ray + 5 * np + i));
+        // queue traffic is read once: streaming loads keep it from evicting the scene
+        const double4 a = ld_rec32_cs(wf.q + i), b = ld_rec32_cs(reinterpret_cast<const char *>(wf.q + i) + 32);
+        O = mk(a.x, a.y, a.z);
+        D = mk(b.x, b.y, b.z);
+        pid = (int)(__double_as_longlong(b.w) & 0xffffffffll);
+        if (W_out) *W_out = a.w;
     }
 }
 
@@ -960,14 +967,10 @@ __device__ __forceinline__ void emit_next_rays(const DevScene &sc, const FramePa
     if (lane == 0) slot0 = atomicAdd(ctr + WF_NNEXT, (unsigned int)__popc(m));
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (cont) {
-        const size_t np = (size_t)wf.n_pad;
         const size_t s = slot0 + rank_in(m, lane);
         const d3 nd = vbounce(D, N);                                  // erl:219-221
-        wf.nq_pid[s] = pid;
-        wf.nq_w[s] = W * ((double)sc.n_lights * refl);
-        double *q = wf.nq_ray + s;
-        q[0] = P.x; q[np] = P.y; q[2 * np] = P.z;
-        q[3 * np] = nd.x; q[4 * np] = nd.y; q[5 * np] = nd.z;
+        st_rec32(wf.nq + s, P.x, P.y, P.z, W * ((double)sc.n_lights * refl));
+        st_rec32(reinterpret_cast<char *>(wf.nq + s) + 32, nd.x, nd.y, nd.z, __longlong_as_double((long long)(unsigned int)pid));
     }
 }
 
@@ -994,14 +997,10 @@ __device__ __forceinline__ void emit_hits_and_rays(const DevScene &sc, const Fra
     old = __shfl_sync(0xffffffffu, old, 0);
     if (hit) write_hit(wf.hit_head, wf.hit_tail, (size_t)(unsigned int)old + rank_in(mh, lane), P, N, D, obj, order, pid, W);
     if (cont) {
-        const size_t np = (size_t)wf.n_pad;
         const size_t s = (size_t)(old >> 32) + rank_in(mc, lane);
         const d3 nd = vbounce(D, N);                                  // erl:219-221
-        wf.nq_pid[s] = pid;
-        wf.nq_w[s] = W * ((double)sc.n_lights * refl);
-        double *q = wf.nq_ray + s;
-        q[0] = P.x; q[np] = P.y; q[2 * np] = P.z;
-        q[3 * np] = nd.x; q[4 * np] = nd.y; q[5 * np] = nd.z;
+        st_rec32(wf.nq + s, P.x, P.y, P.z, W * ((double)sc.n_lights * refl));
+        st_rec32(reinterpret_cast<char *>(wf.nq + s) + 32, nd.x, nd.y, nd.z, __longlong_as_double((long long)(unsigned int)pid));
     }
 }
 
@@ -1047,13 +1046,8 @@ __device__ __forceinline__ bool next_chunk(unsigned long long *cursor, unsigned 
 // warp standing still.  Eight arrays (origin, direction, weight, pixel), sixteen entries per line.
 __device__ __forceinline__ void prefetch_path_chunk(const WfBuf &wf, unsigned long long begin, unsigned long long end, int lane)
 {
-    const size_t np = (size_t)wf.n_pad;
-    const int arr = lane & 7;
-    for (unsigned long long e = begin + (unsigned long long)((lane >> 3) * 16); e < end; e += 64) {
-        const void *p = arr < 6 ? (const void *)(wf.q_ray + (size_t)arr * np + e)
-                                : (arr == 6 ? (const void *)(wf.q_w + e) : (const void *)(wf.q_pid + e));
-        prefetch_l2(p);
-    }
+    // two 64-byte rays per 128-byte line
+    for (unsigned long long e = begin + (unsigned long long)(2 * lane); e < end; e += 64) prefetch_l2(wf.q + e);
 }
 
 // Path rays of one bounce: nearest_object_intersecting_ray/2 (erl:300-346) for every ray of
@@ -1236,12 +1230,11 @@ wf_trace_path_refill(const __grid_constant__ DevScene sc, const __grid_constant_
                 const FinishedHit fh = fin[lane];
                 d3 O;
                 bool valid;
-                path_ray_of_index(fp, wf, false, fh.idx, O, D, pid, valid);
+                path_ray_of_index(fp, wf, false, fh.idx, O, D, pid, valid, &W);
                 obj = fh.obj;
                 order = object_order(sc, obj);
                 P = vadd(O, vscale(D, fh.t));
                 N = hit_normal(sc, obj, P);
-                W = path_weight_of_index(wf, false, fh.idx);
             }
             emit_hits_and_rays(sc, fp, wf, bounce, ctr, lane, hit, P, N, D, obj, order, pid, W);
         }
