@@ -517,6 +517,9 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
         WF_ASSERT(sph < sc.n_spheres, "sphere %d of %d (cell %d, bit %d)", sph, sc.n_spheres, cell, k);
         const int code = obj_code(OBJ_SPHERE, sph);
         if (code == skip_obj || code == best.obj) { PROBE(2, 1); continue; }
+        // the FP64 sphere is asked for before the cull decides whether it is needed (nine times of ten it is): the
+        // whole warp waits for this phase, so its longest latency starts as early as the index is known
+        const double4 es = ld_sphere(sc.sph_exact + sph);
         {
             float b, v;
             filter_stage1(f, fs, b, v);
@@ -524,7 +527,7 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
         }
         double t;
         TALLY(exact_sph);
-        if (sphere_exact(ray.O(), ray.D(), ray.a(), ld_sphere(sc.sph_exact + sph), t)) {
+        if (sphere_exact(ray.O(), ray.D(), ray.a(), es, t)) {
             PROBE(5, 1);
             // better() of erl:319 with the list positions fetched only for a tie
             bool win = best.obj < 0 || t < best.t;
