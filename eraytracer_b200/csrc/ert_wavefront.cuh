@@ -547,10 +547,10 @@ __device__ __forceinline__ void grid_exact(const DevScene &sc, const SRay &f, co
 }
 
 // Runs empty cells until the ray holds a cell with spheres and filters those (while-while, like
-// trav_step).  A cell's block sits at an address the DDA computes, so the block of the NEXT cell is
-// asked for (prefetch to L1) as soon as the step arithmetic has its id: its latency overlaps the
-// sphere tests of this cell.  Returns false when the walk is over (the next cell starts beyond the
-// cull distance, or outside the grid); otherwise `surv` marks the filter survivors of cell `cell`
+// trav_step).  A cell's block sits at an address the DDA computes: no dependent fetch stands between
+// the step and the spheres.  (Prefetching the next cell's block — to L1 or L2, one block or both — is
+// within 0.4 % of not prefetching at all: DESIGN.md "dropped".)  Returns false when the walk is over
+// (the next cell starts beyond the cull distance, or outside the grid); otherwise `surv` marks the filter survivors of cell `cell`
 // (overflow entries counted from `obase`) and `te` is where the cell ends: grid_exact on the
 // survivors and grid_leave complete the step.
 template <bool COUNT>
@@ -578,10 +578,6 @@ __device__ __forceinline__ bool grid_find(GridWalk &g, const GridRay &r, const D
         }
         TALLY(cell);
         te = grid_advance(g, r, cg);
-        if (g.id >= 0 && !(te > g.cullk)) {
-            // (to L1 or to L2, one block or both: within 0.4 % of one another on C4 — DESIGN.md "dropped")
-            prefetch_l1(cg.blocks + (size_t)g.id * kBlockU4);
-        }
         if (hd.x) break;
         if (te > g.cullk) { g.id = -1; return false; }
     }
