@@ -130,3 +130,74 @@ def test_blocked_by_the_triage_means_blocked_by_the_reference(scale, offset, exa
         assert not bad.any(), ("triage blocked a ray the reference lights", O[bad][0], P[bad][0], CS[bad][0], rS[bad][0], CT[bad][0], rT[bad][0])
     # the check has teeth: the triage does settle a good share of these margin cases
     assert said > 0.05 * 3 * n, said
+
+
+def plane_exact(O, D, n, dist):
+    """raytracer.erl:461-480 in double."""
+    vd = n[:, 0] * D[:, 0] + n[:, 1] * D[:, 1] + n[:, 2] * D[:, 2]
+    v0 = -((n[:, 0] * O[:, 0] + n[:, 1] * O[:, 1] + n[:, 2] * O[:, 2]) + dist)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = v0 / vd
+    hit = (vd < 0.0) & (t >= 0.001)
+    return hit, t
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (40.0, 1.0e4), (0.3, -50.0)])
+def test_blocked_by_the_triage_with_a_plane_target(scale, offset):
+    """The plane branch of shadow_blocked(): the target's lower bound is the distance to the hit, refused for grazing rays."""
+    rng = np.random.default_rng(11 + int(abs(offset)))
+    n = 400_000
+    u = U
+    said = 0
+    for _ in range(2):
+        O = offset + rng.normal(size=(n, 3)) * scale * 5.0
+        nrm = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-0.5, 0.5, (n, 1))            # un-normalised normals
+        dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        L = scale * 10.0 ** rng.uniform(-0.5, 2.0, n)
+        P = O + dirs * L[:, None]
+        dist = -(nrm[:, 0] * P[:, 0] + nrm[:, 1] * P[:, 1] + nrm[:, 2] * P[:, 2])         # P lies on the plane
+        rS = scale * 10.0 ** rng.uniform(-2, 0.5, n)
+        perp = np.cross(dirs, rng.normal(size=(n, 3))); perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+        q = np.where(rng.random(n) < 0.4, rS * rng.uniform(0.9, 1.05, n), rS * rng.uniform(0.0, 0.999, n))
+        half = np.sqrt(np.maximum(rS * rS - q * q, 0.0))
+        along = np.where(rng.random(n) < 0.5, L + half + scale * rng.normal(size=n) * 10.0 ** rng.uniform(-7, -1, n), L * rng.uniform(0.02, 1.2, n))
+        CS = O + dirs * along[:, None] + perp * q[:, None]
+        cf, Rf, pad, eta = filter_sphere(CS, rS)
+        # shadow_blocked(), plane target
+        f = (P - O).astype(np.float32)
+        fx, fy, fz = f[:, 0], f[:, 1], f[:, 2]
+        l2 = fx * fx + fy * fy + fz * fz
+        inv = (F(1.0) / np.sqrt(l2)).astype(np.float32)
+        inv = (inv * (F(1.0) + rng.integers(-2, 3, n).astype(np.float32) * F(2.0 ** -23))).astype(np.float32)
+        dx, dy, dz = fx * inv, fy * inv, fz * inv
+        of = O.astype(np.float32)
+        ox, oy, oz = of[:, 0], of[:, 1], of[:, 2]
+        ec0 = F(1.01) * (eta + F(1.75) * u * np.maximum(np.maximum(np.abs(ox), np.abs(oy)), np.abs(oz)))
+        nf = nrm.astype(np.float32)
+        nd = nf[:, 0] * dx + nf[:, 1] * dy + nf[:, 2] * dz
+        ok = np.abs(nd) > F(1e-3) * np.sqrt(nf[:, 0] * nf[:, 0] + nf[:, 1] * nf[:, 1] + nf[:, 2] * nf[:, 2])
+        s_lo = l2 * inv * (F(1.0) - F(1e-5)) - F(1e-7)
+        cx, cy, cz = cf[:, 0] - ox, cf[:, 1] - oy, cf[:, 2] - oz
+        rho2 = cx * cx + cy * cy + cz * cz
+        rho = np.sqrt(rho2)
+        b = dx * cx + dy * cy + dz * cz
+        qx, qy, qz = cy * dz - cz * dy, cz * dx - cx * dz, cx * dy - cy * dx
+        err = ec0 + F(26.0) * u * rho
+        qmax = np.sqrt(qx * qx + qy * qy + qz * qz) * (F(1.0) + F(8.0) * u) + err
+        noise = F(1e-12) * rho2
+        T = ((Rf - pad) * (F(1.0) - F(7.62939453125e-6)) - F(8.0) * u * Rf) - qmax * qmax * (F(1.0) + F(4.0) * u) - F(8.0) * u * Rf
+        sure = (T > F(0.0004) + noise) & (b - err > np.sqrt(Rf) * (F(1.0) + F(4.0) * u))
+        s_up = b + err - np.sqrt(np.maximum(T, F(0))) * (F(1.0) - F(4.0) * u)
+        s_up = s_up + (F(4.0) * u * b + F(4e-6) * np.abs(s_up) + noise + F(1e-7))
+        blocked = ok & sure & (s_up < s_lo)
+        # the reference
+        d = P - O
+        mag = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+        D = d * (1.0 / mag)[:, None]
+        hitS, tS = sphere_exact(O, D, CS, rS)
+        hitP, tP = plane_exact(O, D, nrm, dist)
+        ref_blocked = ~hitP | (hitS & (tS < tP))
+        bad = blocked & ~ref_blocked
+        said += int(blocked.sum())
+        assert not bad.any(), ("triage blocked a ray the reference lights", O[bad][0], P[bad][0], CS[bad][0], rS[bad][0], nrm[bad][0])
+    assert said > 0.05 * 2 * n, said
