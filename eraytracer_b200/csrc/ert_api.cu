@@ -1198,6 +1198,7 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
     int *d_ord = nullptr;
     cudaStream_t st = scene->slots[0].stream;
     int rc = ERT_OK;
+    bool timed = false;
     cudaError_t e;
 #define TRY(call)                                         \
     do {                                                  \
@@ -1212,8 +1213,11 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
     TRY(cudaMemcpyAsync(d_rays, rays6, (size_t)n_rays * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
     {
         unsigned blocks = (unsigned)((n_rays + 255) / 256);
-        Slot &sl0 = scene->slots[0];                 // the kernel's device time is left in slot 0's stats.kernel_ms
-        TRY(cudaEventRecord(sl0.ev0, st));
+        // the kernel's device time is left in slot 0's stats.kernel_ms (unless a frame is in flight there: its
+        // events are not touched)
+        Slot &sl0 = scene->slots[0];
+        timed = !sl0.busy;
+        if (timed) TRY(cudaEventRecord(sl0.ev0, st));
         switch (accel) {
         case ERT_ACCEL_WARP:
             if (n_rays > (1ll << 26)) { rc = fail(ERT_ERR_BADARG, "ERT_ACCEL_WARP takes at most 2^26 rays per call"); goto done; }
@@ -1227,11 +1231,11 @@ int ert_trace_rays(ert_scene *scene, int64_t n_rays, const double *rays6, int ac
         }
     }
     TRY(cudaGetLastError());
-    TRY(cudaEventRecord(scene->slots[0].ev1, st));
+    if (timed) TRY(cudaEventRecord(scene->slots[0].ev1, st));
     TRY(cudaMemcpyAsync(order_out, d_ord, (size_t)n_rays * sizeof(int), cudaMemcpyDeviceToHost, st));
     TRY(cudaMemcpyAsync(t_out, d_t, (size_t)n_rays * sizeof(double), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
-    {
+    if (timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, scene->slots[0].ev0, scene->slots[0].ev1) == cudaSuccess) scene->slots[0].stats.kernel_ms = ms;
     }
