@@ -9,8 +9,10 @@
 %% rounded to binary32 (so a double-precision CPU evaluation and the GPU start from the same
 %% numbers).  List order: the three lights, the spheres, the floor plane.
 %%
-%% NOTE: written without an Erlang/OTP installation (none in the build image); it has not
-%% been compiled or run.  The Python generator is the tested one (tests/test_host.py).
+%% NOTE: written without an Erlang/OTP installation (none in the build image): it has never been
+%% compiled by erlc.  It IS evaluated by oracle/erlref.py (the Erlang evaluator the reference's own
+%% run_tests/0 passes under), and scene(c3) equals the Python generator's scene value for value
+%% (tests/test_erl_reference.py::test_erlang_scene_generator_equals_the_python_generator).
 -module(raytracer_gpu_scenes).
 -export([scene/1, scene/3, splitmix64/2]).
 

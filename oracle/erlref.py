@@ -22,10 +22,13 @@ must return `ok` (tests/test_erl_reference.py).  The images it renders from the 
 the golden vectors of tests/golden/erl_reference.json.
 
 Supported subset: everything raytracer.erl uses outside processes and distribution (no `receive`
-evaluation, no spawn/pool; those forms are parsed, not run).
+evaluation, no spawn/pool; those forms are parsed, not run), plus what erl/raytracer_gpu_scenes.erl needs:
+based integer literals (16#FF), band/bor/bxor/bsl/bsr on unbounded integers, min/max, and whole-byte
+float / unsigned-integer binary segments (`<<F:32/float>> = <<X:32/float>>` rounds to binary32 as BEAM does).
 """
 import math
 import re
+import struct
 import sys
 
 
@@ -73,6 +76,8 @@ def _type_rank(v):
         return 3
     if isinstance(v, list):
         return 4
+    if isinstance(v, bytes):
+        return 5
     raise ErlError("no term order for %r" % (v,))
 
 
@@ -112,6 +117,8 @@ def exact_eq(a, b):
         return len(a) == len(b) and all(exact_eq(x, y) for x, y in zip(a, b))
     if isinstance(a, list) and isinstance(b, list):
         return len(a) == len(b) and all(exact_eq(x, y) for x, y in zip(a, b))
+    if isinstance(a, bytes) and isinstance(b, bytes):
+        return a == b
     return a is b
 
 
@@ -130,13 +137,14 @@ def mk_bool(b):
 # --------------------------------------------------------------------------- tokens
 _TOKEN = re.compile(r"""
     (?P<ws>\s+|%[^\n]*)
+  | (?P<bint>\d+\#[0-9a-zA-Z]+)
   | (?P<float>\d+\.\d+(?:[eE][+-]?\d+)?)
   | (?P<int>\d+)
   | (?P<var>[A-Z_][A-Za-z0-9_@]*)
   | (?P<atom>[a-z][A-Za-z0-9_@]*)
   | '(?P<qatom>(?:[^'\\]|\\.)*)'
   | "(?P<string>(?:[^"\\]|\\.)*)"
-  | (?P<op>->|<-|\|\||=:=|=/=|==|/=|=<|>=|\+\+|--|[()\[\]{},;.|#=<>+\-*/!:?])
+  | (?P<op><<|>>|->|<-|\|\||=:=|=/=|==|/=|=<|>=|\+\+|--|[()\[\]{},;.|#=<>+\-*/!:?])
 """, re.X)
 
 KEYWORDS = {"case", "of", "end", "if", "fun", "when", "receive", "after", "begin", "and", "or", "not", "div", "rem",
@@ -151,7 +159,10 @@ def tokenize(text):
             raise ErlError("cannot tokenise at line %d: %r" % (line, text[pos:pos + 30]))
         kind = m.lastgroup
         s = m.group(0)
-        if kind == "float":
+        if kind == "bint":
+            base, digits = s.split("#")
+            out.append(("int", int(digits, int(base)), line))
+        elif kind == "float":
             out.append(("float", float(s), line))
         elif kind == "int":
             out.append(("int", int(s), line))
@@ -454,6 +465,19 @@ class Parser:
                 return ("rec_new", rec, self.rec_fields())
             if val == "?":
                 return ("macro", self.next()[1])
+            if val == "<<":
+                segs = []
+                while not self.at("op", ">>"):
+                    value = self.expr_primary()
+                    size, typ = None, "integer"
+                    if self.accept("op", ":"):
+                        size = self.expect("int")[1]
+                    if self.accept("op", "/"):
+                        typ = self.expect("atom")[1]
+                    segs.append((value, size, typ))
+                    self.accept("op", ",")
+                self.expect("op", ">>")
+                return ("bin", segs)
         if kind == "kw":
             if val == "case":
                 subject = self.expr()
@@ -594,6 +618,30 @@ class Module:
             return exact_eq(-pat[2][1], val)
         if k == "macro":
             return self.match(self.macros[pat[1]], val, env)
+        if k == "bin":
+            # <<Var:Size/Type, ...>> against a binary: whole-byte float and unsigned big-endian integer segments
+            if not isinstance(val, bytes):
+                return False
+            pos = 0
+            for value, size, typ in pat[1]:
+                size = (64 if typ == "float" else 8) if size is None else size
+                if size % 8 or pos + size // 8 > len(val):
+                    return False
+                chunk = val[pos:pos + size // 8]
+                pos += size // 8
+                if typ == "float":
+                    if size not in (32, 64):
+                        return False
+                    v = struct.unpack(">f" if size == 32 else ">d", chunk)[0]
+                    if math.isinf(v) or math.isnan(v):
+                        return False                 # BEAM does not match non-finite floats
+                elif typ == "integer":
+                    v = int.from_bytes(chunk, "big")
+                else:
+                    raise ErlError("unsupported binary segment type %s" % typ)
+                if not self.match(value, v, env):
+                    return False
+            return pos == len(val)
         raise ErlError("unsupported pattern %r" % (pat,))
 
     def guard_ok(self, guard, env):
@@ -730,6 +778,26 @@ class Module:
             return out
         if k == "macro":
             return self.eval(self.macros[e[1]], env)
+        if k == "bin":
+            out = b""
+            for value, size, typ in e[1]:
+                v = self.eval(value, env)
+                size = (64 if typ == "float" else 8) if size is None else size
+                if typ == "float":
+                    self.need_num(v)
+                    if size not in (32, 64):
+                        raise ErlError("badarg: float segment of %d bits" % size)
+                    try:
+                        out += struct.pack(">f" if size == 32 else ">d", float(v))     # round to nearest even, like BEAM
+                    except OverflowError:
+                        raise ErlError("badarg: float does not fit the segment")
+                elif typ == "integer":
+                    if not isinstance(v, int) or size % 8:
+                        raise ErlError("badarg: integer segment")
+                    out += (v & ((1 << size) - 1)).to_bytes(size // 8, "big")
+                else:
+                    raise ErlError("unsupported binary segment type %s" % typ)
+            return out
         if k == "andalso":
             return self.eval(e[2], env) if erl_bool(self.eval(e[1], env)) else FALSE
         if k == "orelse":
@@ -797,6 +865,11 @@ class Module:
             return mk_bool(exact_eq(a, b))
         if op == "=/=":
             return mk_bool(not exact_eq(a, b))
+        if op in ("band", "bor", "bxor", "bsl", "bsr"):
+            if not (isinstance(a, int) and isinstance(b, int)) or isinstance(a, bool) or isinstance(b, bool):
+                raise ErlError("badarith: %r %s %r" % (a, op, b))
+            return {"band": a & b, "bor": a | b, "bxor": a ^ b, "bsl": a << b if op == "bsl" else 0,
+                    "bsr": a >> b if op == "bsr" else 0}[op]
         if op == "and":
             return mk_bool(erl_bool(a) and erl_bool(b))
         if op == "or":
@@ -847,6 +920,10 @@ class Module:
             return int(args[0].text() if isinstance(args[0], ErlString) else "".join(chr(c) for c in args[0]))
         if fname == "list_to_atom":
             return Atom(args[0].text() if isinstance(args[0], ErlString) else "".join(chr(c) for c in args[0]))
+        if fname == "min":
+            return args[0] if term_cmp(args[0], args[1]) <= 0 else args[1]
+        if fname == "max":
+            return args[0] if term_cmp(args[0], args[1]) >= 0 else args[1]
         if fname == "is_integer":
             return mk_bool(isinstance(args[0], int))
         if fname == "is_float":

@@ -167,3 +167,42 @@ def test_gpu_nearest_hits_equal_the_references(gpu, name):
             assert np.array_equal(t[hit], want_t[hit]), accel
     finally:
         dev.close()
+
+
+# ------------------------------------------------------------------ the Erlang scene generator of erl/ 
+def test_erlang_scene_generator_equals_the_python_generator():
+    """erl/raytracer_gpu_scenes.erl cannot be compiled here (no OTP); it is EVALUATED by oracle/erlref.py — the
+    evaluator the reference's own run_tests/0 passes under — and scene(c3) must equal, value for value, what
+    eraytracer_b200/scene.py generates for the tests and the bench (splitmix64 on 64-bit integers, binary32 rounding
+    through <<X:32/float>>, list order lights / spheres / plane)."""
+    from oracle import erlref
+    from eraytracer_b200 import scene as sc
+    sys.setrecursionlimit(200000)
+    root = os.path.dirname(HERE)
+    with open(os.path.join(root, "erl", "raytracer_gpu_scenes.erl")) as fh:
+        m = erlref.Module(fh.read(), name="raytracer_gpu_scenes")
+    # the generator's primitives
+    assert m.call("splitmix64", 0xE7A9C0DE00000003, 1) == 0xFAD5B148BCB3FFF2
+    u = sc.splitmix64_uniform(0xE7A9C0DE00000003, 40)
+    assert [m.call("uniform", 0xE7A9C0DE00000003, k + 1) for k in range(40)] == [float(x) for x in u]
+    scene = erlref.to_py(m.call("scene", erlref.Atom("c3")))
+    flat = sc.synthetic_scene("c3")
+    assert scene[0] == ["camera", ["vector", 0.0, 0.0, -2.0], ["vector", 0.0, 0.0, 0.0], 90.0, ["screen", 4.0, 2.25]]
+    lights, spheres, plane = scene[1:4], scene[4:-1], scene[-1]
+    assert len(spheres) == len(flat.spheres) == 10000
+    for k, l in enumerate(lights):
+        assert l[0] == "point_light"
+        assert l[1][1:] == [float(x) for x in flat.lights[k]["diffuse_colour"]]
+        assert l[2][1:] == [float(x) for x in flat.lights[k]["location"]]
+        assert l[3][1:] == [float(x) for x in flat.lights[k]["specular_colour"]]
+    got = np.array([[s[1]] + s[2][1:] + s[3][1][1:] + s[3][2:] for s in spheres], dtype=np.float64)
+    want = np.concatenate([flat.spheres["radius"][:, None], flat.spheres["center"], flat.spheres["material"]["colour"],
+                           flat.spheres["material"]["specular_power"][:, None], flat.spheres["material"]["shininess"][:, None],
+                           flat.spheres["material"]["reflectivity"][:, None]], axis=1)
+    assert all(s[0] == "sphere" and s[2][0] == "vector" and s[3][0] == "material" for s in spheres)
+    assert np.array_equal(got, want)                                  # every double, bit for bit
+    assert plane[0] == "plane" and plane[1][1:] == [float(x) for x in flat.planes[0]["normal"]]
+    assert plane[2] == float(flat.planes[0]["distance"])
+    pm = flat.planes[0]["material"]
+    assert plane[3][1][1:] == [float(x) for x in pm["colour"]]
+    assert plane[3][2:] == [float(pm["specular_power"]), float(pm["shininess"]), float(pm["reflectivity"])]
