@@ -9,8 +9,12 @@
 %%     tracing_function(gpu_distributed) -> fun raytracer_gpu:raytraced_pixel_list_gpu_distributed/4;
 %% after which   erl -noinput -run raytracer standalone 1920 1080 out.ppm 1 gpu   works.
 %%
-%% NOTE: written without an Erlang/OTP installation (none in the build image); it has not
-%% been compiled.  It contains no logic beyond argument guards and calls into the NIF.
+%% NOTE: written without an Erlang/OTP installation (none in the build image): it has never been
+%% compiled by erlc or loaded by a BEAM.  Its sequential functions ARE evaluated by oracle/erlref.py
+%% (the Erlang evaluator the reference's own run_tests/0 passes under) with stand-ins for the NIFs:
+%% the tracing function returns the reference's pixel list, error tuples become exits, and
+%% write_binary_to_ppm/4 writes the reference writer's text (tests/test_erl_reference.py).
+%% render_binary/5 (one process per GPU: spawn_link / receive) is parsed, not run.
 -module(raytracer_gpu).
 -export([raytraced_pixel_list_gpu/4,
          raytraced_pixel_list_gpu_distributed/4,

@@ -24,7 +24,10 @@ the golden vectors of tests/golden/erl_reference.json.
 Supported subset: everything raytracer.erl uses outside processes and distribution (no `receive`
 evaluation, no spawn/pool; those forms are parsed, not run), plus what erl/raytracer_gpu_scenes.erl needs:
 based integer literals (16#FF), band/bor/bxor/bsl/bsr on unbounded integers, min/max, and whole-byte
-float / unsigned-integer binary segments (`<<F:32/float>> = <<X:32/float>>` rounds to binary32 as BEAM does).
+float / unsigned-integer binary segments (`<<F:32/float>> = <<X:32/float>>` rounds to binary32 as BEAM does);
+and what erl/raytracer_gpu.erl needs: `$c` literals, `float-native` / `Rest/binary` segments, binary generators in
+list comprehensions, exit/1, is_list/1, integer_to_list/1, proplists:get_value, io_lib:format, file:write_file, and
+`Module.externals` — Python stand-ins for NIFs.
 """
 import math
 import re
@@ -61,6 +64,14 @@ TRUE, FALSE = Atom("true"), Atom("false")
 
 class ErlError(Exception):
     pass
+
+
+class ErlExit(ErlError):
+    """exit(Reason)"""
+
+    def __init__(self, reason):
+        ErlError.__init__(self, "exit: %r" % (reason,))
+        self.reason = reason
 
 
 def _type_rank(v):
@@ -137,6 +148,7 @@ def mk_bool(b):
 # --------------------------------------------------------------------------- tokens
 _TOKEN = re.compile(r"""
     (?P<ws>\s+|%[^\n]*)
+  | (?P<char>\$(?:\\.|[^\\\s]))
   | (?P<bint>\d+\#[0-9a-zA-Z]+)
   | (?P<float>\d+\.\d+(?:[eE][+-]?\d+)?)
   | (?P<int>\d+)
@@ -144,7 +156,7 @@ _TOKEN = re.compile(r"""
   | (?P<atom>[a-z][A-Za-z0-9_@]*)
   | '(?P<qatom>(?:[^'\\]|\\.)*)'
   | "(?P<string>(?:[^"\\]|\\.)*)"
-  | (?P<op><<|>>|->|<-|\|\||=:=|=/=|==|/=|=<|>=|\+\+|--|[()\[\]{},;.|#=<>+\-*/!:?])
+  | (?P<op><<|>>|<=|->|<-|\|\||=:=|=/=|==|/=|=<|>=|\+\+|--|[()\[\]{},;.|#=<>+\-*/!:?])
 """, re.X)
 
 KEYWORDS = {"case", "of", "end", "if", "fun", "when", "receive", "after", "begin", "and", "or", "not", "div", "rem",
@@ -159,7 +171,11 @@ def tokenize(text):
             raise ErlError("cannot tokenise at line %d: %r" % (line, text[pos:pos + 30]))
         kind = m.lastgroup
         s = m.group(0)
-        if kind == "bint":
+        if kind == "char":
+            esc = {"s": " ", "n": "\n", "t": "\t", "\\": "\\", "r": "\r"}
+            ch = esc.get(s[2], s[2]) if s[1] == "\\" else s[1]
+            out.append(("int", ord(ch), line))
+        elif kind == "bint":
             base, digits = s.split("#")
             out.append(("int", int(digits, int(base)), line))
         elif kind == "float":
@@ -439,6 +455,8 @@ class Parser:
                         pat = self.expr()
                         if self.accept("op", "<-"):
                             quals.append(("gen", pat, self.expr()))
+                        elif self.accept("op", "<="):
+                            quals.append(("bgen", pat, self.expr()))
                         else:
                             self.i = save
                             quals.append(("filter", self.expr()))
@@ -473,7 +491,10 @@ class Parser:
                     if self.accept("op", ":"):
                         size = self.expect("int")[1]
                     if self.accept("op", "/"):
-                        typ = self.expect("atom")[1]
+                        specs = [self.expect("atom")[1]]
+                        while self.accept("op", "-"):
+                            specs.append(self.expect("atom")[1])
+                        typ = "-".join(specs)
                     segs.append((value, size, typ))
                     self.accept("op", ",")
                 self.expect("op", ">>")
@@ -538,7 +559,8 @@ class Module:
     def __init__(self, text, name="raytracer"):
         self.name = name
         self.records = {}
-        self.macros = {}
+        self.macros = {"MODULE": ("atom", name)}
+        self.externals = {}    # (name, arity) -> Python callable standing in for a NIF (tests)
         self.functions = {}
         self.out = []          # io:format output (stdout)
         self.files = {}        # filename -> list of written chunks
@@ -556,6 +578,9 @@ class Module:
         return self.apply_local(fname, list(args))
 
     def apply_local(self, fname, args):
+        ext = self.externals.get((fname, len(args)))
+        if ext is not None:
+            return ext(*args)
         clauses = self.functions.get((fname, len(args)))
         if clauses is None:
             raise ErlError("undef: %s/%d" % (fname, len(args)))
@@ -624,21 +649,30 @@ class Module:
                 return False
             pos = 0
             for value, size, typ in pat[1]:
-                size = (64 if typ == "float" else 8) if size is None else size
+                kind, order = self.seg_type(typ)
+                if kind == "binary" and size is None:
+                    chunk = val[pos:]                # Rest/binary: the tail
+                    pos = len(val)
+                    if not self.match(value, chunk, env):
+                        return False
+                    continue
+                size = (64 if kind == "float" else 8) if size is None else size
+                if kind == "binary":
+                    size *= 8
                 if size % 8 or pos + size // 8 > len(val):
                     return False
                 chunk = val[pos:pos + size // 8]
                 pos += size // 8
-                if typ == "float":
+                if kind == "float":
                     if size not in (32, 64):
                         return False
-                    v = struct.unpack(">f" if size == 32 else ">d", chunk)[0]
+                    v = struct.unpack(order + ("f" if size == 32 else "d"), chunk)[0]
                     if math.isinf(v) or math.isnan(v):
                         return False                 # BEAM does not match non-finite floats
-                elif typ == "integer":
-                    v = int.from_bytes(chunk, "big")
+                elif kind == "integer":
+                    v = int.from_bytes(chunk, "big" if order == ">" else "little")
                 else:
-                    raise ErlError("unsupported binary segment type %s" % typ)
+                    v = chunk
                 if not self.match(value, v, env):
                     return False
             return pos == len(val)
@@ -782,21 +816,25 @@ class Module:
             out = b""
             for value, size, typ in e[1]:
                 v = self.eval(value, env)
-                size = (64 if typ == "float" else 8) if size is None else size
-                if typ == "float":
+                kind, order = self.seg_type(typ)
+                if kind == "binary":
+                    if not isinstance(v, bytes):
+                        raise ErlError("badarg: binary segment")
+                    out += v if size is None else v[:size]
+                    continue
+                size = (64 if kind == "float" else 8) if size is None else size
+                if kind == "float":
                     self.need_num(v)
                     if size not in (32, 64):
                         raise ErlError("badarg: float segment of %d bits" % size)
                     try:
-                        out += struct.pack(">f" if size == 32 else ">d", float(v))     # round to nearest even, like BEAM
+                        out += struct.pack(order + ("f" if size == 32 else "d"), float(v))   # round to nearest even, like BEAM
                     except OverflowError:
                         raise ErlError("badarg: float does not fit the segment")
-                elif typ == "integer":
+                else:
                     if not isinstance(v, int) or size % 8:
                         raise ErlError("badarg: integer segment")
-                    out += (v & ((1 << size) - 1)).to_bytes(size // 8, "big")
-                else:
-                    raise ErlError("unsupported binary segment type %s" % typ)
+                    out += (v & ((1 << size) - 1)).to_bytes(size // 8, "big" if order == ">" else "little")
             return out
         if k == "andalso":
             return self.eval(e[2], env) if erl_bool(self.eval(e[1], env)) else FALSE
@@ -816,9 +854,26 @@ class Module:
                 local = dict(env)
                 if self.match(q[1], item, local):
                     self.lc(template, quals, qi + 1, local, out)
+        elif q[0] == "bgen":
+            data = self.eval(q[2], env)
+            if not isinstance(data, bytes) or q[1][0] != "bin":
+                raise ErlError("bad binary generator")
+            width = sum(((64 if self.seg_type(t)[0] == "float" else 8) if sz is None else sz) for _v, sz, t in q[1][1]) // 8
+            for k in range(0, len(data) - width + 1, width):
+                local = dict(env)
+                if self.match(q[1], data[k:k + width], local):
+                    self.lc(template, quals, qi + 1, local, out)
         else:
             if erl_bool(self.eval(q[1], env)):
                 self.lc(template, quals, qi + 1, env, out)
+
+    @staticmethod
+    def seg_type(typ):
+        """'float-native' -> ('float', byte order char for struct); default big-endian like Erlang."""
+        parts = typ.split("-")
+        kind = next((p for p in parts if p in ("integer", "float", "binary")), "integer")
+        order = "<" if ("little" in parts or ("native" in parts and sys.byteorder == "little")) else ">"
+        return kind, order
 
     @staticmethod
     def need_num(v):
@@ -920,6 +975,13 @@ class Module:
             return int(args[0].text() if isinstance(args[0], ErlString) else "".join(chr(c) for c in args[0]))
         if fname == "list_to_atom":
             return Atom(args[0].text() if isinstance(args[0], ErlString) else "".join(chr(c) for c in args[0]))
+        if fname in ("is_list", "is_atom", "is_tuple", "is_binary", "is_number"):
+            kinds = {"is_list": list, "is_atom": Atom, "is_tuple": tuple, "is_binary": bytes, "is_number": (int, float)}
+            return mk_bool(isinstance(args[0], kinds[fname]) and not isinstance(args[0], bool))
+        if fname == "exit":
+            raise ErlExit(args[0])
+        if fname == "integer_to_list":
+            return ErlString(ord(c) for c in str(args[0]))
         if fname == "min":
             return args[0] if term_cmp(args[0], args[1]) <= 0 else args[1]
         if fname == "max":
@@ -996,6 +1058,27 @@ class Module:
             else:
                 dev = args[0]
                 self.files[dev[1]].append(self.format(args[1], args[2]))
+            return Atom("ok")
+        if mod == "erlang" and fname == "nif_error":
+            raise ErlError("nif_error: %r" % (args[0],))
+        if mod == "erlang" and fname in ("min", "max", "exit", "is_list", "integer_to_list"):
+            return self.bif(fname, args)
+        if mod == "proplists" and fname == "get_value":
+            for item in args[1]:
+                if isinstance(item, tuple) and len(item) == 2 and exact_eq(item[0], args[0]):
+                    return item[1]
+            return args[2] if len(args) > 2 else Atom("undefined")
+        if mod == "io_lib" and fname == "format":
+            return ErlString(ord(c) for c in self.format(args[0], args[1]))
+        if mod == "file" and fname == "write_file":
+            def flat(x):
+                if isinstance(x, bytes):
+                    return x.decode("latin-1")
+                if isinstance(x, int):
+                    return chr(x)
+                return "".join(flat(y) for y in x)
+            name = args[0].text() if isinstance(args[0], ErlString) else "".join(chr(c) for c in args[0])
+            self.files[name] = [flat(args[1])]
             return Atom("ok")
         if mod == "file":
             if fname == "open":

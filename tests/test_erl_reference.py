@@ -206,3 +206,62 @@ def test_erlang_scene_generator_equals_the_python_generator():
     pm = flat.planes[0]["material"]
     assert plane[3][1][1:] == [float(x) for x in pm["colour"]]
     assert plane[3][2:] == [float(pm["specular_power"]), float(pm["shininess"]), float(pm["reflectivity"])]
+
+
+# ------------------------------------------------------------------ the Erlang host module of erl/ (boundary)
+def _host_module():
+    from oracle import erlref
+    sys.setrecursionlimit(200000)
+    root = os.path.dirname(HERE)
+    with open(os.path.join(root, "erl", "raytracer_gpu.erl")) as fh:
+        return erlref, erlref.Module(fh.read(), name="raytracer_gpu")
+
+
+@needs_reference
+def test_erlang_tracing_function_returns_the_references_pixel_list():
+    """erl/raytracer_gpu.erl cannot be loaded by a BEAM here; its sequential functions are EVALUATED by oracle/erlref.py
+    with the NIFs replaced by stand-ins that answer what the real ones answer (scene_upload -> {ok, Handle},
+    render_pixel_list -> the reference's own raytraced_pixel_list_simple/4 under the same evaluator).  The tracing
+    function must then return the reference's list — clause order, guards, ok_or_exit/1 and the case are the module's."""
+    erlref, host = _host_module()
+    _, ref = _module()
+    A = erlref.Atom
+    scene = ref.call("scene")
+    host.externals[("scene_upload", 2)] = lambda sc_, dev: (A("ok"), ("handle", sc_))
+    host.externals[("render_pixel_list", 5)] = lambda h, w, hh, d, opts: ref.call("raytraced_pixel_list_simple", w, hh, h[1], d)
+    got = host.call("raytraced_pixel_list_gpu", 8, 6, scene, 2)
+    want = ref.call("raytraced_pixel_list_simple", 8, 6, scene, 2)
+    assert len(got) == 48 and erlref.exact_eq(got, want)
+    assert host.call("raytraced_pixel_list_gpu", 0, 0, scene, 2) == A("done")          # erl:86-87
+    assert host.call("raytraced_pixel_list_gpu_distributed", 0, 0, scene, 2) == A("done")
+    with pytest.raises(erlref.ErlError, match="function_clause"):                    # the guards of erl:88-89
+        host.call("raytraced_pixel_list_gpu", -1, 6, scene, 2)
+    # an error tuple from the NIF becomes exit({raytracer_gpu, Reason})
+    reason = (A("no_device"), 100, erlref.ErlString(ord(c) for c in "no CUDA device"))
+    host.externals[("scene_upload", 2)] = lambda sc_, dev: (A("error"), reason)
+    with pytest.raises(erlref.ErlExit) as ei:
+        host.call("raytraced_pixel_list_gpu", 8, 6, scene, 2)
+    assert erlref.exact_eq(ei.value.reason, (A("raytracer_gpu"), reason))
+    host.externals[("scene_upload", 2)] = lambda sc_, dev: (A("ok"), ("handle", sc_))
+    host.externals[("render_pixel_list", 5)] = lambda h, w, hh, d, opts: (A("error"), reason)
+    with pytest.raises(erlref.ErlExit) as ei:
+        host.call("raytraced_pixel_list_gpu", 8, 6, scene, 2)
+    assert erlref.exact_eq(ei.value.reason, (A("raytracer_gpu"), reason))
+
+
+def test_erlang_frame_helpers():
+    """pixel_list_from_f64/3 (native doubles of an F64 frame -> [{Index, {R,G,B}}]), the distributed tracing function on
+    top of it (render_binary/5 replaced by a stand-in: it spawns one process per GPU), and write_binary_to_ppm/4, whose
+    file must be the text the reference's write_pixels_to_ppm/5 writes for the same image."""
+    erlref, host = _host_module()
+    A = erlref.Atom
+    g = GOLD["ppm"]["demo_8x6_d2"]
+    pix = np.array(g["pixels"], dtype=np.float64)
+    got = host.call("pixel_list_from_f64", pix.tobytes(), 0, [])
+    assert erlref.exact_eq(got, [(k, (float(p[0]), float(p[1]), float(p[2]))) for k, p in enumerate(pix)])
+    host.externals[("render_binary", 5)] = lambda w, h, sc_, d, opts: pix.tobytes()
+    assert erlref.exact_eq(host.call("raytraced_pixel_list_gpu_distributed", 8, 6, [], 2), got)
+    frame = np.clip(quantise(pix), 0, 255).astype(np.uint8).tobytes()
+    name = erlref.ErlString(ord(c) for c in "out.ppm")
+    assert host.call("write_binary_to_ppm", 8, 6, frame, name) == A("ok")
+    assert "".join(host.files["out.ppm"]) == g["text"]
