@@ -13,8 +13,9 @@
 %% compiled by erlc or loaded by a BEAM.  Its sequential functions ARE evaluated by oracle/erlref.py
 %% (the Erlang evaluator the reference's own run_tests/0 passes under) with stand-ins for the NIFs:
 %% the tracing function returns the reference's pixel list, error tuples become exits, and
-%% write_binary_to_ppm/4 writes the reference writer's text (tests/test_erl_reference.py).
-%% render_binary/5 (one process per GPU: spawn_link / receive) is parsed, not run.
+%% write_binary_to_ppm/4 writes the reference writer's text, and render_binary/5 (one linked process
+%% per GPU, selective receive) uploads once, clones for the other GPUs and deals the row bands into
+%% one frame under the evaluator's sequential process model (tests/test_erl_reference.py).
 -module(raytracer_gpu).
 -export([raytraced_pixel_list_gpu/4,
          raytraced_pixel_list_gpu_distributed/4,

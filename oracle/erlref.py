@@ -27,7 +27,10 @@ based integer literals (16#FF), band/bor/bxor/bsl/bsr on unbounded integers, min
 float / unsigned-integer binary segments (`<<F:32/float>> = <<X:32/float>>` rounds to binary32 as BEAM does);
 and what erl/raytracer_gpu.erl needs: `$c` literals, `float-native` / `Rest/binary` segments, binary generators in
 list comprehensions, exit/1, is_list/1, integer_to_list/1, proplists:get_value, io_lib:format, file:write_file, and
-`Module.externals` — Python stand-ins for NIFs.
+`Module.externals` — Python stand-ins for NIFs — and a SEQUENTIAL process model for render_binary/5: spawn/spawn_link
+run the fun to completion at the spawn, `!` appends to a mailbox, `receive` takes the first matching message and fails
+if it would have to wait (a valid schedule for programs whose children never wait for their parent; the reference's own
+master/worker drivers are still outside the evaluator).
 """
 import math
 import re
@@ -561,6 +564,9 @@ class Module:
         self.records = {}
         self.macros = {"MODULE": ("atom", name)}
         self.externals = {}    # (name, arity) -> Python callable standing in for a NIF (tests)
+        self._pids = [(Atom("pid"), 0)]             # sequential process model: the running process is the last one
+        self._next_pid = 1
+        self.mailboxes = {self._pids[0]: []}
         self.functions = {}
         self.out = []          # io:format output (stdout)
         self.files = {}        # filename -> list of written chunks
@@ -840,8 +846,27 @@ class Module:
             return self.eval(e[2], env) if erl_bool(self.eval(e[1], env)) else FALSE
         if k == "orelse":
             return TRUE if erl_bool(self.eval(e[1], env)) else self.eval(e[2], env)
-        if k in ("receive", "send"):
-            raise ErlError("processes are outside this evaluator (%s)" % k)
+        if k == "send":
+            # Pid ! Msg in the sequential process model below
+            pid = self.eval(e[1], env)
+            msg = self.eval(e[2], env)
+            if pid not in self.mailboxes:
+                raise ErlError("badarg: send to %r" % (pid,))
+            self.mailboxes[pid].append(msg)
+            return msg
+        if k == "receive":
+            # selective receive from the current process's mailbox: first message (in arrival order) that a
+            # clause accepts.  A process that would have to WAIT is an error here: spawned funs run to completion
+            # at the spawn (one valid schedule of programs whose children never wait for their parent).
+            box = self.mailboxes[self._pids[-1]]
+            for n, msg in enumerate(box):
+                for pat, guard, body in e[1]:
+                    local = dict(env)
+                    if self.match(pat, msg, local) and self.guard_ok(guard, local):
+                        del box[n]
+                        env.update(local)
+                        return self.eval_body(body, env)
+            raise ErlError("receive would block: no matching message in %r" % (box,))
         raise ErlError("unsupported expression %r" % (k,))
 
     def lc(self, template, quals, qi, env, out):
@@ -980,6 +1005,21 @@ class Module:
             return mk_bool(isinstance(args[0], kinds[fname]) and not isinstance(args[0], bool))
         if fname == "exit":
             raise ErlExit(args[0])
+        if fname == "self" and not args:
+            return self._pids[-1]
+        if fname in ("spawn", "spawn_link") and len(args) == 1:
+            pid = (Atom("pid"), self._next_pid)
+            self._next_pid += 1
+            self.mailboxes[pid] = []
+            self._pids.append(pid)
+            try:
+                args[0]()                            # runs to completion here; an exit of a linked child reaches the parent
+            except ErlExit:
+                if fname == "spawn_link":
+                    raise
+            finally:
+                self._pids.pop()
+            return pid
         if fname == "integer_to_list":
             return ErlString(ord(c) for c in str(args[0]))
         if fname == "min":
@@ -1050,6 +1090,10 @@ class Module:
                 return (args[1][:args[0]], args[1][args[0]:])
             if fname == "reverse":
                 return list(reversed(args[0]))
+            if fname == "zip":
+                if len(args[0]) != len(args[1]):
+                    raise ErlError("function_clause: lists:zip/2 of unequal lists")
+                return [(a, b) for a, b in zip(args[0], args[1])]
         if mod == "io" and fname == "format":
             if len(args) == 1:
                 self.out.append(self.format(args[0], []))

@@ -265,3 +265,44 @@ def test_erlang_frame_helpers():
     name = erlref.ErlString(ord(c) for c in "out.ppm")
     assert host.call("write_binary_to_ppm", 8, 6, frame, name) == A("ok")
     assert "".join(host.files["out.ppm"]) == g["text"]
+
+
+def test_erlang_multi_gpu_driver_deals_the_parts_and_returns_the_shared_frame():
+    """render_binary/5 (erl/raytracer_gpu.erl): one upload, clones for the other GPUs, ONE page-locked frame, one linked
+    process per GPU rendering its row bands into it, results collected by selective receive.  Evaluated under the
+    evaluator's sequential process model (a spawned fun runs to completion at the spawn) with stand-ins for the NIFs
+    that record what they are asked and fill the frame the way ert_render places a part's rows."""
+    erlref, host = _host_module()
+    A = erlref.Atom
+    w, h, n_gpus, depth = 8, 40, 4, 3
+    calls = {"upload": [], "clone": [], "render": []}
+    frame = bytearray(w * h * 3)
+
+    def render_into(handle, fr, d, opts):
+        part = next(o[1] for o in opts if isinstance(o, tuple) and o[0] == A("part"))
+        band, n, p = part
+        calls["render"].append((handle, d, part))
+        for y in range(h):
+            if (y // band) % n == p:                                 # the row-band rule of ert_render (band b -> part b % n)
+                frame[y * w * 3:(y + 1) * w * 3] = bytes([p + 1]) * (w * 3)
+        return A("ok")
+
+    host.externals[("device_count", 0)] = lambda: (A("ok"), n_gpus)
+    host.externals[("scene_upload", 2)] = lambda sc_, dev: calls["upload"].append(dev) or (A("ok"), ("handle", dev))
+    host.externals[("scene_clone", 2)] = lambda hd, dev: calls["clone"].append((hd, dev)) or (A("ok"), ("handle", dev))
+    host.externals[("frame_alloc", 3)] = lambda ww, hh, fmt: (A("ok"), ("frame", ww, hh, fmt))
+    host.externals[("render_into", 4)] = render_into
+    host.externals[("frame_binary", 1)] = lambda fr: bytes(frame)
+    out = host.call("render_binary", w, h, [A("scene")], depth, [])
+    assert calls["upload"] == [0] and calls["clone"] == [(("handle", 0), d) for d in (1, 2, 3)]   # built once, copied
+    assert sorted(c[2][2] for c in calls["render"]) == [0, 1, 2, 3]
+    assert all(c[0] == ("handle", c[2][2]) and c[1] == depth and c[2][0] == 8 and c[2][1] == n_gpus for c in calls["render"])
+    assert out == bytes(frame) and 0 not in out                       # every row was rendered by exactly one part
+    rows = np.frombuffer(out, dtype=np.uint8).reshape(h, w * 3)[:, 0]
+    assert rows.tolist() == [(y // 8) % n_gpus + 1 for y in range(h)]
+    # a part that fails takes the caller down with exit({raytracer_gpu, Reason})
+    reason = (A("cuda"), 700, erlref.ErlString(ord(c) for c in "illegal address"))
+    host.externals[("render_into", 4)] = lambda handle, fr, d, opts: (A("error"), reason)
+    with pytest.raises(erlref.ErlExit) as ei:
+        host.call("render_binary", w, h, [A("scene")], depth, [])
+    assert erlref.exact_eq(ei.value.reason, (A("raytracer_gpu"), reason))
